@@ -1,0 +1,139 @@
+/*
+ * umereg_b200 — C ABI of the B200-native UME descriptor-and-registration hot path.
+ *
+ * The reference (yuvalH9/UMERegRobust) has no FFI / plugin boundary: it is pure Python whose
+ * native work happens inside third-party wheels.  This header is therefore the boundary a
+ * maintainer would bind (ctypes stub shown in INTEGRATION.md); every entry point names the
+ * reference call it replaces (file:line into the reference tree).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`; float32 row-major,
+ *     contiguous; nothing is allocated behind the caller's back: scratch memory comes in through
+ *     (`ws`, `ws_bytes`) sized by the matching `*_workspace_bytes` query;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises,
+ *     and is safe to call concurrently from different host threads on different streams with
+ *     different workspaces;
+ *   - return value: UME_OK (0) or a negative ume_status; `ume_last_error()` holds a thread-local
+ *     human-readable message for the last failure.  No exception crosses this boundary.
+ *   - B = clouds in the batch, N = points per cloud, n = keypoints per cloud, C = feature
+ *     channels, K = max neighbours, M = 4 monomials [1,x,y,z].
+ */
+#ifndef UMEREG_B200_H_
+#define UMEREG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UME_ABI_VERSION 1
+
+typedef enum ume_status {
+    UME_OK = 0,
+    UME_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, unsupported C / K        */
+    UME_ERR_WORKSPACE = -2,    /* ws == NULL or ws_bytes too small                          */
+    UME_ERR_UNSUPPORTED = -3,  /* size outside what this build supports (see each function) */
+    UME_ERR_CUDA = -4          /* a CUDA runtime call / kernel launch failed                */
+} ume_status;
+
+/* flags */
+#define UME_FLAG_FMA_DIST      1u  /* dist2 with fused multiply-add (what nvcc -fmad=true makes of
+                                      pytorch3d's CUDA kernel); default: separately rounded mul/add
+                                      (pytorch3d CPU build, torch/numpy restatements)           */
+#define UME_FLAG_CELL_DIV2     2u  /* search grid with cell = radius/2 instead of radius        */
+
+int ume_abi_version(void);
+const char* ume_last_error(void);
+const char* ume_status_string(int status);
+
+/* ---------------------------------------------------------------- neighbour search
+ * Replaces pytorch3d.ops.ball_query as called at evaluate.py:51 and utils/loc_utils.py:383-384:
+ * for every query the FIRST K rows of p2 (in row order) with dist2 < radius^2 (strict).
+ *   p1 (B,P1,3) queries, p2 (B,P2,3) cloud
+ *   idx   (B,P1,K) int64, -1 padded           (may be NULL)
+ *   dists (B,P1,K) squared distances, 0 padded (may be NULL)
+ *   nn    (B,P1,K,3) neighbour xyz, 0 padded   (may be NULL)
+ *   count (B,P1) int32 number of neighbours found (may be NULL)
+ * Limits: K <= 8192, P2 <= 8388608. */
+size_t ume_ball_query_workspace_bytes(int B, int P1, int P2, int K);
+int ume_ball_query_f32(const float* p1, const float* p2, int B, int P1, int P2, int K, float radius,
+                       unsigned flags, int64_t* idx, float* dists, float* nn, int32_t* count,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- fused gather + UME moments
+ * Replaces evaluate.py:50-60 `my_ume_generation` (ball_query + -1 padding + torch.gather of the
+ * (B,n,K,C) neighbour features + the two reductions + normalisation) and the same math in
+ * utils/loc_utils.py:365-372 (`ume_kp_layer.ume_mat`).  The (B,n,K,C) tensor is never formed.
+ *   pts (B,N,3), kpts (B,n,3), feat (B,N,C)
+ *   F   (B,n,C,4)  = [sum f | sum f x^T] / (sum_c sum f + 1e-6), absolute coordinates (as the reference)
+ *   Fc  (B,n,C,4)  same matrix with coordinates relative to the keypoint (may be NULL); it spans
+ *                  the same column space as F and is better conditioned
+ *   count (B,n) int32 neighbours used per keypoint (may be NULL)
+ * Limits: C multiple of 4 in [4,128] or any C <= 256 (slower path); N <= 8388608; any K >= 1. */
+size_t ume_moments_workspace_bytes(int B, int N, int n, int C, int K);
+int ume_moments_f32(const float* pts, const float* kpts, const float* feat, int B, int N, int n,
+                    int C, int K, float radius, unsigned flags, float* F, float* Fc, int32_t* count,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- subspace descriptor
+ * Replaces the two torch.linalg.qr calls of utils/loc_utils.py:9,11 (and :338,341): an
+ * orthonormal basis of the column space of each C x 4 matrix.  The projector Q Q^T does not
+ * depend on the basis chosen, so no particular QR sign convention is reproduced.
+ *   F  (nmat, C, 4)  ->  Qt (nmat, 4, C)   (basis vectors as ROWS: the K-major GEMM operand)
+ * Rank-deficient input: missing directions are completed with canonical unit vectors
+ * (all-zero input gives e0..e3, like LAPACK); `rank` (nmat) int32 may be NULL. */
+int ume_orthonormalize_f32(const float* F, int64_t nmat, int C, float* Qt, int32_t* rank, void* stream);
+
+/* ---------------------------------------------------------------- all-pairs subspace distance
+ * Replaces utils/loc_utils.py:12-13 (P = QQ^T, torch.cdist(P1.flatten, P2.flatten)/sqrt 2) and the
+ * arg-min of evaluate.py:224 through the identity D^2 = 4 - |Q1^T Q2|_F^2.
+ *   Qt1 (B,n1,4,C), Qt2 (B,n2,4,C)
+ *   D      (B,n1,n2) (may be NULL)
+ *   argmin (B,n1) int64 = first index of the row minimum (may be NULL)
+ *   dmin   (B,n1) the row minimum (may be NULL)
+ * `impl`: 0 = fp32 SIMT kernel, 1 = tcgen05 tensor-core kernel (3xTF32 split, fp32-grade).
+ * Limits: C multiple of 4, C <= 128. */
+size_t ume_cdist_workspace_bytes(int B, int n1, int n2, int C, int impl);
+int ume_cdist_f32(const float* Qt1, const float* Qt2, int B, int n1, int n2, int C, int impl, float* D,
+                  int64_t* argmin, float* dmin, void* ws, size_t ws_bytes, void* stream);
+
+/* Distance between CORRESPONDING descriptors: Dp[i] = scale * sqrt(8 - 2 |Q1_i^T Q2_i|_F^2).
+ * utils/loc_utils.py:344 uses scale = 0.707 (literally), ume_cdist uses 1/sqrt(2). */
+int ume_pair_dist_f32(const float* Qt1, const float* Qt2, int64_t nmat, int C, float scale, float* Dp,
+                      void* stream);
+
+/* ---------------------------------------------------------------- rigid solve
+ * Replaces utils/loc_utils.py:292-335,346-350 `batch_estimate_transform_ume_old(G, H)`:
+ * weighted centroids, 3x3 cross moment over the C rows, SVD, det fix, translation.
+ *   G, H: moment matrices, row stride C*4.  Hypothesis i of batch b uses
+ *         G[b, gi[b,i]] and H[b, hi[b,i]]  (gi / hi int64, either may be NULL = identity i)
+ *   nG, nH: matrices per batch entry in G / H;  nm: hypotheses per batch entry
+ *   T (B,nm,4,4): T[:3,:3] = R^T, T[:3,3] = b2  (so tgt ~ T[:3,:3] src + T[:3,3])
+ *   offG (B,nG,3) / offH (B,nH,3) (both or neither NULL): G / H hold moments RELATIVE to these
+ *         points (the `Fc` output of ume_moments_f32); the solve then runs on the small centred
+ *         numbers and t is un-centred at the end. */
+int ume_rigid_solve_f32(const float* G, const float* H, const int64_t* gi, const int64_t* hi,
+                        const float* offG, const float* offH, int B, int nG, int nH, int nm, int C,
+                        float* T, void* stream);
+
+/* ---------------------------------------------------------------- nearest-neighbour feature transfer
+ * Replaces pytorch3d.ops.knn_points(K=1) + knn_gather at evaluate.py:272-275.
+ *   q (B,P1,3) queries, p (B,P2,3) cloud, x (B,P2,U) features of p (may be NULL)
+ *   idx (B,P1) int64 (may be NULL), d2 (B,P1) (may be NULL), out (B,P1,U) = x[idx] (may be NULL)
+ * Ties: the lower row index wins (as a row-order scan with strict '<'). */
+size_t ume_knn1_workspace_bytes(int B, int P1, int P2);
+int ume_knn1_gather_f32(const float* q, const float* p, const float* x, int B, int P1, int P2, int U,
+                        unsigned flags, int64_t* idx, float* d2, float* out, void* ws, size_t ws_bytes,
+                        void* stream);
+
+/* ---------------------------------------------------------------- counters
+ * Number of kernels this library has launched since load (all threads); bench.py reports the
+ * difference over the timed region as `gpu_launches`. */
+uint64_t ume_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UMEREG_B200_H_ */

@@ -1,0 +1,377 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the reference-signature wrappers) against
+the oracle and the committed golden vectors.  Integer results (neighbour indices, arg-min) must be
+bit-exact; floating point within the tolerance written next to each assert."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import pytorch3d_ops as p3d
+from oracle import ume_oracle as orc
+from umeregrobust_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ume():
+    import umeregrobust_b200 as u
+    from umeregrobust_b200 import _lib
+    _lib.lib()                                   # fails loudly when the CUDA library is missing
+    yield u
+    u.config.update(fma_dist=False, cell_div2=False, cdist_impl=0)
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def moment_err(F, F_ref, kappa):
+    num = np.abs(F - F_ref).max(axis=(-1, -2))
+    den = np.maximum(np.abs(F_ref).max(axis=(-1, -2)), 1e-30)
+    return float((num / den / kappa).max())
+
+
+def cloud(seed, B, N, spread=20.0, offset=(30.0, -20.0, 0.0)):
+    rng = np.random.default_rng(seed)
+    p = np.stack([rng.uniform(-spread, spread, (B, N)), rng.uniform(-spread, spread, (B, N)),
+                  rng.uniform(-2, 2, (B, N))], -1) + np.asarray(offset)
+    return p.astype(np.float32), rng
+
+
+# ----------------------------------------------------------------------------- ball_query
+@pytest.mark.parametrize("N,P1,K,radius", [
+    (3000, 97, 16, 2.0),        # K < hits: select path
+    (3000, 64, 500, 2.0),       # K > hits: padding
+    (20000, 40, 750, 6.0),      # hits > list capacity (1024): overflow path, K < hits
+    (20000, 33, 4000, 8.0),     # large K, cap 4096
+    (257, 257, 300, 100.0),     # K > N, everything in radius
+    (500, 5, 1, 0.5),           # K = 1
+])
+@pytest.mark.parametrize("fma,div2", [(False, False), (True, False), (False, True)])
+def test_ball_query_bit_exact(ume, N, P1, K, radius, fma, div2):
+    ume.config.update(fma_dist=fma, cell_div2=div2)
+    p2, rng = cloud(N + P1, 2, N)
+    p1 = p2[:, rng.choice(N, P1, replace=False)].copy()
+    p1[:, ::3] += rng.normal(scale=0.3, size=p1[:, ::3].shape).astype(np.float32)   # some off-cloud queries
+    ref = p3d.ball_query_c(p1, p2, K, radius, fma=fma)
+    out = ume.ball_query(dev(p1), dev(p2), K=K, radius=radius, return_nn=True)
+    assert out.idx.dtype == torch.int64
+    assert np.array_equal(host(out.idx), ref.idx)
+    assert np.array_equal(host(out.dists), ref.dists)
+    assert np.array_equal(host(out.knn), ref.knn)
+    ume.config.update(fma_dist=False, cell_div2=False)
+
+
+def test_ball_query_edge_cases(ume):
+    p2, rng = cloud(5, 1, 1000)
+    # no neighbour at all; radius 0; identical points; query far away
+    far = np.array([[[1e4, 1e4, 1e4], [30, -20, 0]]], np.float32)
+    out = ume.ball_query(dev(far), dev(p2), K=8, radius=1.0)
+    ref = p3d.ball_query_c(far, p2, 8, 1.0)
+    assert np.array_equal(host(out.idx), ref.idx) and (host(out.idx)[0, 0] == -1).all()
+    out = ume.ball_query(dev(p2[:, :10]), dev(p2), K=4, radius=0.0)
+    assert (host(out.idx) == -1).all() and (host(out.dists) == 0).all()
+    same = np.tile(np.array([[[1.0, 2.0, 3.0]]], np.float32), (1, 300, 1))
+    out = ume.ball_query(dev(same[:, :3]), dev(same), K=50, radius=0.1)
+    assert np.array_equal(host(out.idx)[0, 0], np.arange(50))
+    out = ume.ball_query(dev(p2[:, :0]), dev(p2), K=4, radius=1.0)          # no queries
+    assert tuple(out.idx.shape) == (1, 0, 4)
+    with pytest.raises(RuntimeError):
+        ume.ball_query(torch.zeros(1, 2, 3), torch.zeros(1, 5, 3), K=2, radius=1.0)     # CPU tensors: no fallback
+    with pytest.raises(ValueError):
+        ume.ball_query(dev(p2), dev(np.zeros((2, 5, 3), np.float32)), K=2, radius=1.0)  # batch mismatch
+
+
+# ----------------------------------------------------------------------------- moments
+@pytest.mark.parametrize("C", [4, 8, 16, 32, 64, 128, 12, 33, 200])
+def test_moments_all_channel_counts(ume, C):
+    N, n, K, radius = 4000, 48, 200, 3.0
+    pts, rng = cloud(C, 2, N)
+    feat = synth._normalize_rows(rng.normal(size=(2, N, C))).astype(np.float32)
+    kp = pts[:, rng.choice(N, n, replace=False)].copy()
+    F64, idx = orc.ume_moments(pts, kp, feat, K, radius, dtype=np.float64, return_idx=True)
+    kappa = orc.normaliser_condition(feat, idx)
+    F, Fc, cnt = ume.ume_moments(dev(pts), dev(kp), dev(feat), K, radius, return_centered=True, return_count=True)
+    assert np.array_equal(host(cnt), (idx >= 0).sum(-1))
+    assert moment_err(host(F), F64, kappa) < 2e-6              # relative, per unit of normaliser conditioning
+    # centred matrix: F1c = F1 - k F0 (same column space)
+    Fc_ref = F64.copy()
+    Fc_ref[..., 1:] -= kp[:, :, None, :].astype(np.float64) * F64[..., :1]
+    scale = np.abs(F64[..., :1]).max(axis=(-1, -2), keepdims=True) * radius
+    assert float((np.abs(host(Fc) - Fc_ref) / scale / kappa[..., None, None]).max()) < 2e-6
+
+
+@pytest.mark.parametrize("N,n,K,radius", [
+    (30000, 24, 750, 6.0),      # ~4000 hits > list capacity 2048, K < capacity
+    (30000, 16, 3000, 6.0),     # K above the list capacity: chunked flush
+    (30000, 16, 100000, 6.0),   # K > N: every hit used, chunked
+    (2000, 2000, 64, 1.5),      # every point a keypoint
+])
+def test_moments_overflow_and_large_k(ume, N, n, K, radius):
+    pts, rng = cloud(N + K, 1, N, spread=18.0)
+    feat = synth._normalize_rows(rng.normal(size=(1, N, 32))).astype(np.float32)
+    kp = pts[:, rng.choice(N, n, replace=False)].copy()
+    F64, idx = orc.ume_moments(pts, kp, feat, min(K, N), radius, dtype=np.float64, return_idx=True)
+    kappa = orc.normaliser_condition(feat, idx)
+    F, cnt = ume.ume_moments(dev(pts), dev(kp), dev(feat), K, radius, return_count=True)
+    assert np.array_equal(host(cnt), (idx >= 0).sum(-1))
+    assert moment_err(host(F), F64, kappa) < 2e-6
+
+
+def test_moments_fma_mode_changes_only_boundary_points(ume):
+    pts, rng = cloud(77, 1, 20000)
+    feat = synth._normalize_rows(rng.normal(size=(1, 20000, 8))).astype(np.float32)
+    kp = pts[:, :256].copy()
+    for fma in (False, True):
+        ume.config.update(fma_dist=fma)
+        _, idx = orc.ume_moments(pts, kp, feat, 5000, 5.0, return_idx=True, fma=fma)
+        _, cnt = ume.ume_moments(dev(pts), dev(kp), dev(feat), 5000, 5.0, return_count=True)
+        assert np.array_equal(host(cnt), (idx >= 0).sum(-1))
+    ume.config.update(fma_dist=False)
+
+
+# ----------------------------------------------------------------------------- golden: whole hot path
+@pytest.mark.parametrize("name", ["hotpath_noisy", "hotpath_exact"])
+def test_hot_path_against_reference_golden(ume, golden, name):
+    from types import SimpleNamespace
+    g = golden(name)
+    K, radius = int(g["K"]), float(g["radius"])
+    args = SimpleNamespace(ume_max_nn=K, ume_r_nn=radius)
+    sp, sk, sf = dev(g["src_pts"][None]), dev(g["src_kp"][None]), dev(g["src_feat"][None])
+    tp, tk, tf = dev(g["tgt_pts"][None]), dev(g["tgt_kp"][None]), dev(g["tgt_feat"][None])
+    # neighbour indices: bit-exact
+    bq = ume.ball_query(sk, sp, K=K, radius=radius, return_nn=False)
+    assert np.array_equal(host(bq.idx)[0], g["bq_idx_src"][0].astype(np.int64))
+    # moments (evaluate.my_ume_generation)
+    F_src = ume.my_ume_generation(sp, sk, sf, args)
+    F_tgt = ume.my_ume_generation(tp, tk, tf, args)
+    ks = orc.normaliser_condition(g["src_feat"][None], g["bq_idx_src"].astype(np.int64))
+    kt = orc.normaliser_condition(g["tgt_feat"][None], g["bq_idx_tgt"].astype(np.int64))
+    assert moment_err(host(F_src), g["F_src"], ks) < 3e-6
+    assert moment_err(host(F_tgt), g["F_tgt"], kt) < 3e-6
+    # distances on the REFERENCE's matrices, so that each stage is pinned on its own
+    D = host(ume.ume_cdist(dev(g["F_src"]), dev(g["F_tgt"])))
+    D64 = orc.ume_cdist(g["F_src"], g["F_tgt"], dtype=np.float64)
+    assert np.abs(D - D64).max() < 5e-4                      # sqrt amplifies fp32 rounding near D = 0
+    assert np.abs(D - D64)[D64 > 0.05].max() < 2e-5
+    assert np.abs(D - g["D"]).max() < 2e-3                   # the reference's own mm-form cdist noise (SURVEY §4 i)
+    # arg-min: equal to the reference's wherever the best-vs-second gap is above fp32 noise
+    _, am, dm = ume.descriptor_cdist(ume.ume_descriptors(dev(g["F_src"])), ume.ume_descriptors(dev(g["F_tgt"])),
+                                     want_D=False, want_argmin=True)
+    srt = np.sort(D64, -1)
+    clear = (srt[..., 1] - srt[..., 0]) > 1e-4
+    assert clear.mean() > 0.9
+    assert np.array_equal(host(am)[clear], g["match"][..., 1][clear])
+    assert np.array_equal(host(am), np.argmin(D, -1))        # fused arg-min == arg-min of the written D
+    assert np.abs(host(dm) - D.min(-1)).max() == 0
+    # rigid hypotheses from the reference's matched matrices
+    G = g["F_src"][0][g["match"][0, :, 0]]
+    H = g["F_tgt"][0][g["match"][0, :, 1]]
+    T, Dp = ume.batch_estimate_transform_ume_old(dev(G), dev(H))
+    T64, Dp64 = orc.rigid_from_ume(G, H, dtype=np.float64)
+    ang = orc.rotation_angle_rad(host(T)[:, :3, :3], T64[:, :3, :3])
+    ang_ref = orc.rotation_angle_rad(g["T"][:, :3, :3], T64[:, :3, :3])
+    terr = np.abs(host(T)[:, :3, 3] - T64[:, :3, 3]).max(-1)
+    terr_ref = np.abs(g["T"][:, :3, 3] - T64[:, :3, 3]).max(-1)
+    # north_star tolerance 1e-4 rad / 1e-4 m against the fp64 oracle, or the reference's own fp32
+    # distance to that oracle where that is larger (ill-conditioned hypotheses)
+    assert (ang <= np.maximum(1e-4, 2 * ang_ref)).all(), (ang.max(), ang_ref.max())
+    assert (terr <= np.maximum(1e-4, 2 * terr_ref)).all(), (terr.max(), terr_ref.max())
+    assert np.abs(host(Dp) - Dp64).max() < 5e-4
+    assert np.array_equal(host(T)[:, 3], np.tile(np.array([0, 0, 0, 1], np.float32), (len(G), 1)))
+
+
+def test_config1_whole_cloud_exact_recovery(ume, golden):
+    g = golden("config1_whole_cloud")
+    T, _ = ume.batch_estimate_transform_ume_old(dev(g["G"]), dev(g["H"]))
+    T64, _ = orc.rigid_from_ume(g["G"], g["H"], dtype=np.float64)
+    assert orc.rotation_angle_rad(host(T)[0, :3, :3], T64[0, :3, :3]) < 1e-4
+    assert np.abs(host(T)[0, :3, 3] - T64[0, :3, 3]).max() < max(1e-4, 2 * np.abs(g["T"][0, :3, 3] - T64[0, :3, 3]).max())
+    assert orc.rotation_angle_rad(host(T)[0, :3, :3], g["gt"][:3, :3]) < 1e-4
+    # whole-cloud UME through the fused kernel: one "keypoint", radius covering everything
+    for nm in ("src", "tgt"):
+        pts, feat = g[nm + "_pts"][None], g[nm + "_feat"][None]
+        kp = pts[:, :1].copy()
+        F = ume.ume_moments(dev(pts), dev(kp), dev(feat), 4096, 1000.0)
+        ref = orc.moments_from_neighbors(pts.astype(np.float64), feat.astype(np.float64))
+        assert np.abs(host(F)[0, 0] - ref[0]).max() / np.abs(ref).max() < 1e-5
+
+
+def test_rigid_random_golden(ume, golden):
+    g = golden("rigid_random")
+    for C in (8, 32, 64):
+        G, H = g[f"G{C}"], g[f"H{C}"]
+        T, Dp = ume.batch_estimate_transform_ume_old(dev(G), dev(H))
+        T64, D64 = orc.rigid_from_ume(G, H, dtype=np.float64)
+        ang = orc.rotation_angle_rad(host(T)[:, :3, :3], T64[:, :3, :3])
+        terr = np.abs(host(T)[:, :3, 3] - T64[:, :3, 3]).max(-1)
+        ang_ref = orc.rotation_angle_rad(g[f"T{C}"][:, :3, :3], T64[:, :3, :3])
+        terr_ref = np.abs(g[f"T{C}"][:, :3, 3] - T64[:, :3, 3]).max(-1)
+        assert (ang <= np.maximum(1e-4, 2 * ang_ref)).all(), (C, ang.max(), ang_ref.max())
+        assert (terr <= np.maximum(1e-4, 2 * terr_ref)).all(), (C, terr.max(), terr_ref.max())
+        assert np.abs(host(Dp) - D64).max() < 5e-4
+        R = host(T)[:, :3, :3]
+        assert np.abs(R @ np.swapaxes(R, 1, 2) - np.eye(3)).max() < 1e-5
+        assert np.abs(np.linalg.det(R.astype(np.float64)) - 1).max() < 1e-5
+
+
+def test_rigid_degenerate_inputs_are_finite(ume):
+    C = 32
+    rng = np.random.default_rng(9)
+    G = rng.normal(size=(6, C, 4)).astype(np.float32)
+    H = G.copy()
+    G[0] = 0; H[0] = 0                                   # all zero
+    H[1] = 0                                             # zero target
+    G[2, :, 1:] = G[2, :, :1] * np.array([1.0, 2.0, 3.0], np.float32)   # every 'point' identical: rank-1 cross moment
+    H[2] = G[2]
+    H[3] = G[3]                                          # identical pair -> identity transform
+    T, Dp = ume.batch_estimate_transform_ume_old(dev(G), dev(H))
+    T = host(T)
+    assert np.isfinite(T[[0, 2, 3, 4, 5]]).all()
+    R = T[[0, 2, 3], :3, :3]
+    assert np.abs(R @ np.swapaxes(R, 1, 2) - np.eye(3)).max() < 1e-5
+    assert np.abs(T[3] - np.eye(4)).max() < 1e-4
+    assert abs(host(Dp)[3]) < 2e-3
+
+
+# ----------------------------------------------------------------------------- descriptors / distances
+@pytest.mark.parametrize("C,n1,n2", [(32, 100, 70), (8, 33, 65), (64, 40, 40), (4, 17, 9), (128, 20, 31)])
+def test_cdist_against_fp64_oracle(ume, C, n1, n2):
+    rng = np.random.default_rng(C)
+    F1 = rng.normal(size=(2, n1, C, 4)).astype(np.float32)
+    F2 = rng.normal(size=(2, n2, C, 4)).astype(np.float32)
+    F2[:, :5] = F1[:, :5] @ (rng.normal(size=(4, 4)) + 3 * np.eye(4)).astype(np.float32)   # same subspaces -> D ~ 0
+    F1[..., 1:] += 40.0 * F1[..., :1]                     # correlated columns, like absolute coordinates
+    F2[..., 1:] += 40.0 * F2[..., :1]
+    D64 = orc.ume_cdist_gram(F1, F2)
+    if C > 4:
+        assert np.abs(D64 - orc.ume_cdist(F1, F2, dtype=np.float64)).max() < 1e-6
+    D = host(ume.ume_cdist(dev(F1), dev(F2)))
+    assert D.shape == (2, n1, n2)
+    assert np.abs(D - D64)[D64 > 0.05].max() < 5e-5
+    assert np.abs(D - D64).max() < 3e-3
+    assert D.min() >= 0 and D.max() <= 2.0 + 1e-6
+    Qt, rank = ume.ume_descriptors(dev(F1), return_rank=True)
+    Q = host(Qt).astype(np.float64)
+    assert np.abs(Q @ np.swapaxes(Q, -1, -2) - np.eye(4)).max() < 5e-6       # orthonormal rows
+    assert (host(rank) == 4).all()
+
+
+def test_descriptors_rank_deficient(ume):
+    C = 32
+    F = np.zeros((5, C, 4), np.float32)
+    rng = np.random.default_rng(3)
+    v = rng.normal(size=(C, 1)).astype(np.float32)
+    F[1] = v @ np.array([[1.0, 30.0, -20.0, 2.0]], np.float32)                 # rank 1 (a single neighbour)
+    F[2] = rng.normal(size=(C, 4))
+    F[2][:, 3] = F[2][:, 1] * 2 - F[2][:, 0]                                     # rank 3
+    F[3] = rng.normal(size=(C, 4)) * 1e-20                                       # tiny but full rank
+    F[4] = rng.normal(size=(C, 4)) * 1e18                                        # huge but full rank
+    Qt, rank = ume.ume_descriptors(dev(F), return_rank=True)
+    Q = host(Qt).astype(np.float64)
+    assert host(rank).tolist() == [0, 1, 3, 4, 4]
+    assert np.isfinite(Q).all()
+    assert np.abs(Q @ np.swapaxes(Q, -1, -2) - np.eye(4)).max() < 1e-5
+    assert np.array_equal(Q[0], np.eye(4, C))                                    # LAPACK's answer for the zero matrix
+    # the basis still contains the matrix's own column space
+    for i in (1, 2):
+        resid = F[i].astype(np.float64) - Q[i].T @ (Q[i] @ F[i].astype(np.float64))
+        assert np.abs(resid).max() < 1e-4 * np.abs(F[i]).max()
+
+
+# ----------------------------------------------------------------------------- ume_kp_layer
+def test_kp_layer_golden(ume, golden):
+    g = golden("kp_layer")
+    args = [dev(g[k][None]) for k in ("src_pts", "src_feat", "src_kp", "tgt_pts", "tgt_feat", "tgt_kp")]
+    for tag, diag in (("diag", True), ("full", False)):
+        layer = ume.ume_kp_layer(int(g["ume_knn"]), float(g["ume_desc_rad"]), diag_only=diag)
+        T, D, G_kp, H_kp = layer(*args)
+        assert tuple(T.shape) == g["T_" + tag].shape and tuple(D.shape) == g["D_" + tag].shape
+        assert tuple(G_kp.shape) == g["G_" + tag].shape and tuple(H_kp.shape) == g["H_" + tag].shape
+        T64, D64, G64, H64 = orc.ume_kp_layer_forward(
+            *[g[k][None] for k in ("src_pts", "src_feat", "src_kp", "tgt_pts", "tgt_feat", "tgt_kp")],
+            int(g["ume_knn"]), float(g["ume_desc_rad"]), diag_only=diag, dtype=np.float64)
+        assert np.abs(host(G_kp) - g["G_" + tag]).max() / np.abs(g["G_" + tag]).max() < 1e-4
+        assert np.abs(host(D) - D64).max() < 2e-3
+        assert np.abs(host(D) - g["D_" + tag]).max() < 3e-3
+        ang = orc.rotation_angle_rad(host(T)[..., :3, :3], T64[..., :3, :3])
+        ang_ref = orc.rotation_angle_rad(g["T_" + tag][..., :3, :3], T64[..., :3, :3])
+        # both computed from fp32 moment matrices that differ in the last bits: compare through the
+        # reference's own distance to the fp64 result
+        assert np.median(ang) <= max(1e-4, 2 * np.median(ang_ref))
+
+
+# ----------------------------------------------------------------------------- knn (K = 1) transfer
+@pytest.mark.parametrize("N,P1", [(5000, 777), (300, 2000), (1, 10)])
+def test_knn1_bit_exact(ume, N, P1):
+    p2, rng = cloud(N, 2, N)
+    q = (p2[:, rng.integers(0, N, P1)] + rng.normal(scale=0.4, size=(2, P1, 3))).astype(np.float32)
+    q[:, :5] += 500.0                                          # far outside the cloud's box
+    ref = p3d.knn_points_c(q, p2, 1)
+    out = ume.knn_points(dev(q), dev(p2), K=1)
+    assert np.array_equal(host(out.idx), ref.idx)
+    assert np.array_equal(host(out.dists), ref.dists)
+    x = rng.normal(size=(2, N, 7)).astype(np.float32)
+    got = host(ume.knn1_transfer(dev(q), dev(p2), dev(x)))
+    assert np.array_equal(got, p3d.knn_gather_np(x, ref.idx)[:, :, 0])
+    assert np.array_equal(host(ume.knn_gather(dev(x), out.idx)), p3d.knn_gather_np(x, ref.idx))
+
+
+def test_knn1_ties_lower_index_wins(ume):
+    rng = np.random.default_rng(4)
+    p2 = rng.integers(-3, 3, size=(1, 400, 3)).astype(np.float32)          # duplicated lattice points
+    q = rng.integers(-3, 3, size=(1, 100, 3)).astype(np.float32)
+    ref = p3d.knn_points_c(q, p2, 1)
+    out = ume.knn_points(dev(q), dev(p2), K=1)
+    assert np.array_equal(host(out.idx), ref.idx)
+
+
+# ----------------------------------------------------------------------------- fused pipeline
+def test_register_hypotheses_exact_copy_recovers_gt(ume):
+    p = synth.make_pair(5, N=20000, C=32, n_kp=128, exact_copy=True, generator="disc")
+    d = {k: dev(v[None]) for k, v in p.items() if k.endswith(("pts", "feat", "kp"))}
+    for centered in (True, False):
+        out = ume.register_hypotheses(d["src_pts"], d["src_feat"], d["src_kp"], d["tgt_pts"], d["tgt_feat"],
+                                      d["tgt_kp"], 750, 5.0, want_D=True, centered=centered)
+        assert np.array_equal(host(out["match"])[0, :, 1], np.arange(128))       # every keypoint matches itself
+        T = host(out["T"])[0]
+        ang = orc.rotation_angle_rad(T[:, :3, :3], p["gt"][:3, :3].astype(np.float64))
+        terr = np.abs(T[:, :3, 3] - p["gt"][:3, 3]).max(-1)
+        # the moved cloud is itself rounded to fp32 (~4e-6 m at 50 m), identical neighbour sets
+        assert ang.max() < (1e-4 if centered else 5e-4), ang.max()
+        assert terr.max() < (1e-3 if centered else 5e-3), terr.max()
+    ref = orc.register_pair_hypotheses(p["src_pts"][None], p["src_feat"][None], p["src_kp"][None], p["tgt_pts"][None],
+                                       p["tgt_feat"][None], p["tgt_kp"][None], 750, 5.0, dtype=np.float64)
+    assert np.array_equal(host(out["match"]), ref["match"])
+
+
+def test_register_hypotheses_matches_oracle_noisy_pair(ume):
+    p = synth.make_pair(6, N=20000, C=32, n_kp=256, generator="disc")
+    d = {k: dev(v[None]) for k, v in p.items() if k.endswith(("pts", "feat", "kp"))}
+    ref = orc.register_pair_hypotheses(p["src_pts"][None], p["src_feat"][None], p["src_kp"][None], p["tgt_pts"][None],
+                                       p["tgt_feat"][None], p["tgt_kp"][None], 750, 5.0, dtype=np.float64)
+    out = ume.register_hypotheses(d["src_pts"], d["src_feat"], d["src_kp"], d["tgt_pts"], d["tgt_feat"], d["tgt_kp"],
+                                  750, 5.0, want_D=True)
+    D64 = ref["D"]
+    assert np.abs(host(out["D"]) - D64).max() < 1e-3
+    srt = np.sort(D64, -1)
+    clear = (srt[..., 1] - srt[..., 0]) > 1e-4
+    assert clear.mean() > 0.95
+    assert np.array_equal(host(out["match"])[..., 1][clear], ref["match"][..., 1][clear])
+    same = host(out["match"])[..., 1] == ref["match"][..., 1]
+    T, T64 = host(out["T"])[same], ref["T"][same]
+    ang = orc.rotation_angle_rad(T[:, :3, :3], T64[:, :3, :3])
+    terr = np.abs(T[:, :3, 3] - T64[:, :3, 3]).max(-1)
+    # (R,t) within 1e-4 rad / 1e-4 m of the fp64 oracle for well-conditioned hypotheses; the
+    # conditioning of a hypothesis is measured by the reference's own fp32 deviation
+    ref32 = orc.register_pair_hypotheses(p["src_pts"][None], p["src_feat"][None], p["src_kp"][None], p["tgt_pts"][None],
+                                         p["tgt_feat"][None], p["tgt_kp"][None], 750, 5.0, dtype=np.float32)
+    same32 = same & (ref32["match"][..., 1] == ref["match"][..., 1])
+    ang32 = orc.rotation_angle_rad(ref32["T"][same32][:, :3, :3], ref["T"][same32][:, :3, :3])
+    assert np.median(ang) < 1e-4 and np.median(terr) < 1e-4, (np.median(ang), np.median(terr))
+    assert np.percentile(ang, 90) <= max(1e-4, 2 * np.percentile(ang32, 90))

@@ -1,0 +1,389 @@
+"""Host-side mirror of the reference's call signatures for the UME hot path.
+
+Every function here has the name, argument meaning and return layout of the reference function it
+replaces (file:line cited per function) and does its work in libumereg_b200.so (hand-written
+sm_100a CUDA behind the C ABI of include/umereg_b200.h).  torch is used for device memory,
+streams and nothing else.  Inputs must be CUDA tensors: there is no CPU fallback.
+"""
+import collections
+import ctypes
+
+import torch
+
+from . import _lib
+
+_BallQuery = collections.namedtuple("_BallQuery", ["dists", "idx", "knn"])
+_KNN = collections.namedtuple("_KNN", ["dists", "idx", "knn"])
+
+# Global defaults (can be changed by callers / tests):
+#   fma_dist : evaluate the squared distance with fused multiply-adds (what nvcc makes of
+#              pytorch3d's CUDA kernel) instead of separately rounded mul/add (pytorch3d CPU build)
+#   cell_div2: search grid with cell = radius / 2
+#   cdist_impl: 0 = fp32 SIMT distance kernel, 1 = tcgen05 tensor-core kernel
+config = {"fma_dist": False, "cell_div2": False, "cdist_impl": 0}
+
+_workspaces = {}
+
+
+def _flags():
+    return (_lib.UME_FLAG_FMA_DIST if config["fma_dist"] else 0) | (_lib.UME_FLAG_CELL_DIV2 if config["cell_div2"] else 0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _workspace(nbytes, device):
+    """Per (device, stream) scratch buffer, grown on demand.  Calls are stream-ordered, so reuse
+    by consecutive calls on the same stream is safe."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _dev_f32(t, name, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s is on %s: umeregrobust_b200 only runs on CUDA devices (no CPU fallback)" % (name, t.device))
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("%s must have %d dims, got shape %s" % (name, ndim, tuple(t.shape)))
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------- pytorch3d names
+def ball_query(p1, p2, lengths1=None, lengths2=None, K=500, radius=0.2, return_nn=True):
+    """pytorch3d.ops.ball_query as called at evaluate.py:51 and utils/loc_utils.py:383-384:
+    first K rows of p2 (row order) with dist^2 < radius^2; idx -1 padded (int64), dists 0 padded,
+    knn zero padded.  Returns a namedtuple (dists, idx, knn)."""
+    if lengths1 is not None or lengths2 is not None:
+        raise NotImplementedError("ball_query: heterogeneous lengths are not used by the reference and not supported")
+    p1 = _dev_f32(p1, "p1", 3)
+    p2 = _dev_f32(p2, "p2", 3)
+    if p1.shape[0] != p2.shape[0] or p1.shape[2] != 3 or p2.shape[2] != 3:
+        raise ValueError("ball_query: p1 %s and p2 %s must be (B,P,3) with equal B" % (tuple(p1.shape), tuple(p2.shape)))
+    B, P1, _ = p1.shape
+    P2 = p2.shape[1]
+    K = int(K)
+    idx = torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
+    dists = torch.empty((B, P1, K), dtype=torch.float32, device=p1.device)
+    nn = torch.empty((B, P1, K, 3), dtype=torch.float32, device=p1.device) if return_nn else None
+    with torch.cuda.device(p1.device):
+        L = _lib.lib()
+        nbytes = L.ume_ball_query_workspace_bytes(B, P1, P2, K)
+        ws = _workspace(nbytes, p1.device)
+        rc = L.ume_ball_query_f32(_ptr(p1), _ptr(p2), B, P1, P2, K, float(radius), _flags(), _ptr(idx), _ptr(dists),
+                                  _ptr(nn), None, _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "ball_query")
+    return _BallQuery(dists, idx, nn)
+
+
+def knn_points(p1, p2, lengths1=None, lengths2=None, norm=2, K=1, version=-1, return_nn=False, return_sorted=True):
+    """pytorch3d.ops.knn_points for the K = 1 case the hot path uses (evaluate.py:272,274):
+    (dists (B,P1,1) squared L2, idx (B,P1,1) int64, knn or None)."""
+    if lengths1 is not None or lengths2 is not None:
+        raise NotImplementedError("knn_points: heterogeneous lengths are not supported")
+    if norm != 2:
+        raise NotImplementedError("knn_points: only norm=2")
+    if int(K) != 1:
+        raise NotImplementedError("knn_points: only K=1 (evaluate.py:272-275) is on this path")
+    p1 = _dev_f32(p1, "p1", 3)
+    p2 = _dev_f32(p2, "p2", 3)
+    if p1.shape[0] != p2.shape[0]:
+        raise ValueError("knn_points: batch sizes differ")
+    B, P1, _ = p1.shape
+    P2 = p2.shape[1]
+    idx = torch.empty((B, P1, 1), dtype=torch.int64, device=p1.device)
+    d2 = torch.empty((B, P1, 1), dtype=torch.float32, device=p1.device)
+    with torch.cuda.device(p1.device):
+        L = _lib.lib()
+        ws = _workspace(L.ume_knn1_workspace_bytes(B, P1, P2), p1.device)
+        rc = L.ume_knn1_gather_f32(_ptr(p1), _ptr(p2), None, B, P1, P2, 0, _flags(), _ptr(idx), _ptr(d2), None,
+                                   _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "knn_points")
+    knn = knn_gather(p2, idx) if return_nn else None
+    return _KNN(d2, idx, knn)
+
+
+def knn_gather(x, idx, lengths=None):
+    """pytorch3d.ops.knn_gather (evaluate.py:273,275; utils/loc_utils.py:354,581): x (B,M,U),
+    idx (B,L,K) -> (B,L,K,U).  Pure indexing (pytorch3d implements it as expand+gather too)."""
+    B, M, U = x.shape
+    _, Lq, K = idx.shape
+    flat = idx.reshape(B, Lq * K, 1).expand(-1, -1, U)
+    return torch.gather(x, 1, flat).reshape(B, Lq, K, U)
+
+
+def knn1_transfer(q, p, x):
+    """Fused evaluate.py:272-273 (and :274-275): features of the nearest row of `p` for every row
+    of `q`: knn_gather(x, knn_points(q, p, K=1).idx)[:, :, 0, :] without the index round trip."""
+    q = _dev_f32(q, "q", 3)
+    p = _dev_f32(p, "p", 3)
+    x = _dev_f32(x, "x", 3)
+    B, P1, _ = q.shape
+    P2, U = x.shape[1], x.shape[2]
+    if p.shape[1] != P2 or p.shape[0] != B or x.shape[0] != B:
+        raise ValueError("knn1_transfer: shapes do not agree")
+    out = torch.empty((B, P1, U), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        L = _lib.lib()
+        ws = _workspace(L.ume_knn1_workspace_bytes(B, P1, P2), q.device)
+        rc = L.ume_knn1_gather_f32(_ptr(q), _ptr(p), _ptr(x), B, P1, P2, U, _flags(), None, None, _ptr(out),
+                                   _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "knn1_transfer")
+    return out
+
+
+# ----------------------------------------------------------------------------- UME moments
+def ume_moments(pts, kpts, feat, K, radius, return_centered=False, return_count=False):
+    """Fused ball-query + gather + moment build.  F (B,n,C,4) exactly as evaluate.py:50-60
+    produces it; optionally the keypoint-centred matrix Fc (same column space) and the
+    neighbour count per keypoint."""
+    pts = _dev_f32(pts, "pts", 3)
+    kpts = _dev_f32(kpts, "kpts", 3)
+    feat = _dev_f32(feat, "feat", 3)
+    B, N, _ = pts.shape
+    if kpts.shape[0] != B or feat.shape[0] != B or feat.shape[1] != N or pts.shape[2] != 3 or kpts.shape[2] != 3:
+        raise ValueError("ume_moments: pts %s, kpts %s, feat %s do not agree" %
+                         (tuple(pts.shape), tuple(kpts.shape), tuple(feat.shape)))
+    n, C = kpts.shape[1], feat.shape[2]
+    dev = pts.device
+    F = torch.empty((B, n, C, 4), dtype=torch.float32, device=dev)
+    Fc = torch.empty_like(F) if return_centered else None
+    cnt = torch.empty((B, n), dtype=torch.int32, device=dev) if return_count else None
+    with torch.cuda.device(dev):
+        L = _lib.lib()
+        ws = _workspace(L.ume_moments_workspace_bytes(B, N, n, C, int(K)), dev)
+        rc = L.ume_moments_f32(_ptr(pts), _ptr(kpts), _ptr(feat), B, N, n, C, int(K), float(radius), _flags(),
+                               _ptr(F), _ptr(Fc), _ptr(cnt), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "ume_moments")
+    out = (F,)
+    if return_centered:
+        out += (Fc,)
+    if return_count:
+        out += (cnt,)
+    return out[0] if len(out) == 1 else out
+
+
+def my_ume_generation(pts, kpts, feat, args):
+    """evaluate.py:50-60 `my_ume_generation(pts, kpts, feat, args)` -> F (B,n,C,4); reads
+    args.ume_max_nn and args.ume_r_nn.  (The reference hard-codes C = 32 at :55; any C works here.)"""
+    return ume_moments(pts, kpts, feat, args.ume_max_nn, args.ume_r_nn)
+
+
+def create_local_ume_matrix(nn_pts, nn_feat):
+    """utils/loc_utils.py:434-445: un-normalised moments of pre-gathered neighbourhoods
+    (bs, n_kp, pc, 3) / (bs, n_kp, pc, C).  Kept as plain batched torch matmuls: it is an unused
+    helper in the reference (no caller in any script) and not part of the measured path."""
+    F1 = nn_feat.transpose(-1, -2) @ nn_pts
+    F0 = nn_feat.transpose(-1, -2).sum(dim=-1, keepdim=True)
+    return torch.cat([F0, F1], dim=-1)
+
+
+# ----------------------------------------------------------------------------- descriptors / distances
+def ume_descriptors(ume, return_rank=False):
+    """Orthonormal basis rows Qt (..., 4, C) of the column space of each (..., C, 4) UME matrix
+    (the QR of utils/loc_utils.py:9,11 up to the choice of basis)."""
+    ume = _dev_f32(ume, "ume")
+    if ume.dim() < 2 or ume.shape[-1] != 4:
+        raise ValueError("ume_descriptors: expected (..., C, 4), got %s" % (tuple(ume.shape),))
+    C = ume.shape[-2]
+    nmat = ume.numel() // (C * 4) if C > 0 else 0
+    Qt = torch.empty(ume.shape[:-2] + (4, C), dtype=torch.float32, device=ume.device)
+    rank = torch.empty(ume.shape[:-2], dtype=torch.int32, device=ume.device) if return_rank else None
+    with torch.cuda.device(ume.device):
+        rc = _lib.lib().ume_orthonormalize_f32(_ptr(ume), nmat, C, _ptr(Qt), _ptr(rank), _stream())
+    _lib.check(rc, "ume_descriptors")
+    return (Qt, rank) if return_rank else Qt
+
+
+def descriptor_cdist(Qt1, Qt2, want_D=True, want_argmin=False, impl=None):
+    """All-pairs D = sqrt(4 - |Q1^T Q2|_F^2) between descriptor sets (B,n1,4,C) x (B,n2,4,C), with
+    the row arg-min (first index on ties) fused.  Returns (D or None, argmin or None, dmin or None)."""
+    Qt1 = _dev_f32(Qt1, "Qt1", 4)
+    Qt2 = _dev_f32(Qt2, "Qt2", 4)
+    B, n1, _, C = Qt1.shape
+    n2 = Qt2.shape[1]
+    if Qt2.shape[0] != B or Qt2.shape[3] != C or Qt1.shape[2] != 4 or Qt2.shape[2] != 4:
+        raise ValueError("descriptor_cdist: shapes %s and %s do not agree" % (tuple(Qt1.shape), tuple(Qt2.shape)))
+    impl = config["cdist_impl"] if impl is None else impl
+    dev = Qt1.device
+    D = torch.empty((B, n1, n2), dtype=torch.float32, device=dev) if want_D else None
+    am = torch.empty((B, n1), dtype=torch.int64, device=dev) if want_argmin else None
+    dm = torch.empty((B, n1), dtype=torch.float32, device=dev) if want_argmin else None
+    with torch.cuda.device(dev):
+        L = _lib.lib()
+        nbytes = L.ume_cdist_workspace_bytes(B, n1, n2, C, impl)
+        ws = _workspace(nbytes, dev) if nbytes else None
+        rc = L.ume_cdist_f32(_ptr(Qt1), _ptr(Qt2), B, n1, n2, C, impl, _ptr(D), _ptr(am), _ptr(dm), _ptr(ws),
+                             ws.numel() if ws is not None else 0, _stream())
+    _lib.check(rc, "descriptor_cdist")
+    return D, am, dm
+
+
+def ume_cdist(ume1, ume2):
+    """utils/loc_utils.py:8-15 `ume_cdist(ume1, ume2)`: (bs,n1,C,4) x (bs,n2,C,4) -> D (bs,n1,n2),
+    D_ij = |P1_i - P2_j|_F / sqrt(2) with P = Q Q^T."""
+    if ume1.dim() != 4 or ume2.dim() != 4:
+        raise ValueError("ume_cdist: expected (bs, n, C, 4) tensors")
+    D, _, _ = descriptor_cdist(ume_descriptors(ume1), ume_descriptors(ume2), want_D=True, want_argmin=False)
+    return D
+
+
+# ----------------------------------------------------------------------------- rigid solve
+def rigid_solve(G, H, gi=None, hi=None, offG=None, offH=None):
+    """Batched closed-form rigid hypotheses.  G (B,nG,C,4), H (B,nH,C,4); hypothesis (b,i) pairs
+    G[b,gi[b,i]] with H[b,hi[b,i]] (identity when the index is None).  offG/offH: the points the
+    moments are relative to (for the centred `Fc` matrices).  Returns T (B,nm,4,4)."""
+    G = _dev_f32(G, "G", 4)
+    H = _dev_f32(H, "H", 4)
+    B, nG, C, _ = G.shape
+    nH = H.shape[1]
+    if H.shape[0] != B or H.shape[2] != C or G.shape[3] != 4 or H.shape[3] != 4:
+        raise ValueError("rigid_solve: shapes %s and %s do not agree" % (tuple(G.shape), tuple(H.shape)))
+    if gi is not None:
+        gi = gi.to(torch.int64).contiguous()
+    if hi is not None:
+        hi = hi.to(torch.int64).contiguous()
+    nm = gi.shape[1] if gi is not None else (hi.shape[1] if hi is not None else min(nG, nH))
+    if offG is not None:
+        offG = _dev_f32(offG, "offG", 3)
+        offH = _dev_f32(offH, "offH", 3)
+    T = torch.empty((B, nm, 4, 4), dtype=torch.float32, device=G.device)
+    with torch.cuda.device(G.device):
+        rc = _lib.lib().ume_rigid_solve_f32(_ptr(G), _ptr(H), _ptr(gi), _ptr(hi), _ptr(offG), _ptr(offH), B, nG, nH,
+                                            nm, C, _ptr(T), _stream())
+    _lib.check(rc, "rigid_solve")
+    return T
+
+
+def batch_estimate_transform_ume_old(G, H):
+    """utils/loc_utils.py:292-350 `batch_estimate_transform_ume_old(G, H)`: G, H (bs, C, 4) ->
+    (T (bs,4,4), D (bs,)) with T[:3,:3] = R^T, T[:3,3] = b2 and D = 0.707 |P_H - P_G|_F."""
+    if G.dim() != 3 or H.dim() != 3 or G.shape != H.shape or G.shape[-1] != 4:
+        raise ValueError("batch_estimate_transform_ume_old: G %s, H %s must both be (bs, C, 4)" %
+                         (tuple(G.shape), tuple(H.shape)))
+    G = _dev_f32(G, "G")
+    H = _dev_f32(H, "H")
+    bs, C, _ = G.shape
+    T = rigid_solve(G[None], H[None])[0]
+    Dp = torch.empty((bs,), dtype=torch.float32, device=G.device)
+    if bs:
+        Qg = ume_descriptors(G)
+        Qh = ume_descriptors(H)
+        with torch.cuda.device(G.device):
+            rc = _lib.lib().ume_pair_dist_f32(_ptr(Qh), _ptr(Qg), bs, C, 0.707, _ptr(Dp), _stream())
+        _lib.check(rc, "batch_estimate_transform_ume_old")
+    return T, Dp
+
+
+def relative_rotation_error(R, R_hat):
+    """utils/eval_utils.py:60-76: degrees, acos((clamp(tr(R_hat R^T), -1, 3) - 1) / 2).  A handful
+    of elementwise torch ops on (B,3,3); a metric, not part of the measured path."""
+    delta = torch.matmul(R_hat, torch.transpose(R, 1, 2))
+    tr = torch.clamp(torch.einsum("bii->b", delta), -1, 3)
+    return torch.acos((tr - 1) / 2) * (180 / torch.tensor(3.141592653589793))
+
+
+# ----------------------------------------------------------------------------- ume_kp_layer
+def ball_query_gather(pts, idx):
+    """utils/loc_utils.py:353-354: rows of pts at idx with a zero row for idx == -1."""
+    pad = torch.cat((torch.zeros((pts.shape[0], 1, pts.shape[-1]), device=pts.device, dtype=pts.dtype), pts), 1)
+    return knn_gather(pad, idx + 1)
+
+
+class ume_kp_layer(torch.nn.Module):
+    """utils/loc_utils.py:357-431.  Same constructor and forward signature; forward returns
+    (T, D, G_kp, H_kp) with T (bs,n_kp[,n_kp],4,4) and D (bs,n_kp[,n_kp])."""
+
+    def __init__(self, ume_knn, ume_desc_rad, diag_only=False, n_rand=None):
+        super().__init__()
+        self.ume_knn = ume_knn
+        self.ume_desc_rad = ume_desc_rad
+        self.diag_only = diag_only
+        self.n_rand = n_rand
+
+    def ume_mat(self, points, features, bs, n_kp):
+        """:365-372 on pre-gathered, zero-padded neighbourhoods (bs*n_kp, K, 3/C)."""
+        m0 = torch.sum(features, dim=1, keepdim=True)
+        m1 = features.transpose(2, 1) @ points
+        mat = torch.cat((m0.transpose(2, 1), m1), dim=2) / (torch.sum(m0, dim=-1, keepdim=True) + 1e-6)
+        return mat.view(bs, n_kp, *mat.shape[1:])
+
+    def batch_keypoints(self, points, idx):
+        out = ball_query_gather(points, idx)
+        return out.view(-1, *out.shape[2:])
+
+    def forward(self, source_points, source_features, source_kp, target_points, target_features, target_kp):
+        bs, n_kp = source_kp.shape[0], source_kp.shape[1]
+        # :383-393 ball_query + gathers + ume_mat, fused (no (bs,n_kp,K,C) tensor)
+        G = ume_moments(source_points, source_kp, source_features, self.ume_knn, self.ume_desc_rad)
+        H = ume_moments(target_points, target_kp, target_features, self.ume_knn, self.ume_desc_rad)
+        C = G.shape[-2]
+        if self.n_rand is not None:
+            # :406-410 random triplet sums (host RNG, "only valid for batch size of one")
+            import numpy as np
+            if not self.diag_only:
+                Gf = G.unsqueeze(2).expand(bs, n_kp, n_kp, C, 4).reshape(-1, C, 4)
+                Hf = H.unsqueeze(1).expand(bs, n_kp, n_kp, C, 4).reshape(-1, C, 4)
+            else:
+                Gf, Hf = G.reshape(-1, C, 4), H.reshape(-1, C, 4)
+            tri = torch.from_numpy(np.random.choice(np.arange(Gf.shape[0]), (self.n_rand, 3))).to(G.device)
+            Gf = Gf[tri[:, 0]] + Gf[tri[:, 1]] + Gf[tri[:, 2]]
+            Hf = Hf[tri[:, 0]] + Hf[tri[:, 1]] + Hf[tri[:, 2]]
+            T, D = batch_estimate_transform_ume_old(Gf, Hf)
+            return T.view(bs, -1, 4, 4), D.view(bs, -1), G.unsqueeze(2).squeeze(), H.unsqueeze(1).squeeze()
+        if self.diag_only:
+            T = rigid_solve(G, H)                                          # pairs i <-> i
+            Qg, Qh = ume_descriptors(G), ume_descriptors(H)
+            D = torch.empty((bs, n_kp), dtype=torch.float32, device=G.device)
+            with torch.cuda.device(G.device):
+                rc = _lib.lib().ume_pair_dist_f32(_ptr(Qh), _ptr(Qg), bs * n_kp, C, 0.707, _ptr(D), _stream())
+            _lib.check(rc, "ume_kp_layer")
+        else:
+            # all n_kp^2 pairs (:394-397) without materialising the broadcast (bs*n_kp^2, C, 4) tensors
+            ar = torch.arange(n_kp, device=G.device)
+            gi = ar.repeat_interleave(n_kp).unsqueeze(0).expand(bs, -1).contiguous()
+            hi = ar.repeat(n_kp).unsqueeze(0).expand(bs, -1).contiguous()
+            T = rigid_solve(G, H, gi, hi).view(bs, n_kp, n_kp, 4, 4)
+            D, _, _ = descriptor_cdist(ume_descriptors(G), ume_descriptors(H))
+            D = D * (0.707 * 2.0 ** 0.5)                                    # :344 uses 0.707, not 1/sqrt(2)
+        return T, D, G.unsqueeze(2).squeeze(), H.unsqueeze(1).squeeze()
+
+
+# ----------------------------------------------------------------------------- fused hot path
+def register_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K, radius, want_D=False,
+                        centered=True):
+    """evaluate.py:206-257 for a whole batch, without the host-RNG sub-sampling (:233-245): UME
+    matrices for both clouds, subspace distances with fused arg-min, one rigid hypothesis per
+    source keypoint from its best-matching target keypoint.
+
+    centered=True runs descriptors and the solve on the keypoint-centred moments (same column
+    space / same transform, smaller numbers, closer to the exact answer than the reference's own
+    fp32); centered=False follows the reference's absolute-coordinate arithmetic.
+    Returns dict(F_src, F_tgt, match (B,n,2) int64, dmin (B,n), T (B,n,4,4), D or None)."""
+    if centered:
+        F_src, Fc_src = ume_moments(src_pts, src_kp, src_feat, K, radius, return_centered=True)
+        F_tgt, Fc_tgt = ume_moments(tgt_pts, tgt_kp, tgt_feat, K, radius, return_centered=True)
+        A, Bm = Fc_src, Fc_tgt
+    else:
+        F_src = ume_moments(src_pts, src_kp, src_feat, K, radius)
+        F_tgt = ume_moments(tgt_pts, tgt_kp, tgt_feat, K, radius)
+        A, Bm = F_src, F_tgt
+    D, am, dm = descriptor_cdist(ume_descriptors(A), ume_descriptors(Bm), want_D=want_D, want_argmin=True)
+    if centered:
+        T = rigid_solve(A, Bm, None, am, src_kp, tgt_kp)
+    else:
+        T = rigid_solve(A, Bm, None, am)
+    B, n = am.shape
+    match = torch.stack([torch.arange(n, device=am.device).expand(B, n), am], dim=-1)
+    return dict(F_src=F_src, F_tgt=F_tgt, match=match, dmin=dm, T=T, D=D)

@@ -1,0 +1,233 @@
+// Search-grid construction: bins each cloud's points into uniform cells around the queries.
+// HBM-bound integer/byte work: one coalesced pass to count, one to scatter.
+#include "ume_common.cuh"
+
+#include <float.h>
+
+namespace ume {
+
+namespace {
+
+UME_DEVI int float_order_key(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+UME_DEVI float float_from_key(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+__global__ void grid_init_kernel(int* __restrict__ bbox, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * 6) bbox[i] = (i % 6 < 3) ? INT_MAX : INT_MIN;   // [min xyz | max xyz] as ordered keys
+}
+
+__global__ void grid_bbox_kernel(const float* __restrict__ q, int nq, int* __restrict__ bbox) {
+    const int b = blockIdx.y;
+    const float* qb = q + (size_t)b * nq * 3;
+    int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+        float x = qb[i * 3 + 0], y = qb[i * 3 + 1], z = qb[i * 3 + 2];
+        if (isfinite(x) && isfinite(y) && isfinite(z)) {
+            int kx = float_order_key(x), ky = float_order_key(y), kz = float_order_key(z);
+            mn[0] = min(mn[0], kx); mx[0] = max(mx[0], kx);
+            mn[1] = min(mn[1], ky); mx[1] = max(mx[1], ky);
+            mn[2] = min(mn[2], kz); mx[2] = max(mx[2], kz);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        mn[d] = __reduce_min_sync(UME_FULL_MASK, mn[d]);
+        mx[d] = __reduce_max_sync(UME_FULL_MASK, mx[d]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            atomicMin(&bbox[b * 6 + d], mn[d]);
+            atomicMax(&bbox[b * 6 + 3 + d], mx[d]);
+        }
+    }
+}
+
+__global__ void grid_params_kernel(const int* __restrict__ bbox, GridHeader* __restrict__ hdr, int B,
+                                   float expand, float cell, int cells_cap) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    GridHeader h;
+    float lo[3], hi[3];
+    bool valid = true;
+    float amax = 0.f;
+    for (int d = 0; d < 3; ++d) {
+        int kmin = bbox[b * 6 + d], kmax = bbox[b * 6 + 3 + d];
+        if (kmin == INT_MAX || kmax == INT_MIN) valid = false;
+        lo[d] = float_from_key(kmin);
+        hi[d] = float_from_key(kmax);
+        amax = fmaxf(amax, fmaxf(fabsf(lo[d]), fabsf(hi[d])));
+    }
+    const float r = fabsf(expand);
+    if (!valid || !isfinite(r)) {
+        // no usable query: an empty domain (nothing passes x >= +inf)
+        h.ox = h.oy = h.oz = INFINITY;
+        h.hx = h.hy = h.hz = -INFINITY;
+        h.inv_s = 1.f; h.s = 1.f; h.nx = h.ny = h.nz = 1; h.ncells = 1; h.n_sorted = 0;
+        h.pad[0] = h.pad[1] = h.pad[2] = 0;
+        hdr[b] = h;
+        return;
+    }
+    const float margin = r * 1e-3f + amax * 1e-5f + 1e-6f;
+    float ext[3];
+    for (int d = 0; d < 3; ++d) {
+        lo[d] -= (r + margin);
+        hi[d] += (r + margin);
+        ext[d] = hi[d] - lo[d];
+    }
+    float emax = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
+    float s = cell;
+    if (!(s > 0.f)) {
+        // automatic: the finest grid the table allows (the loop below coarsens it until it fits)
+        const float fl = emax * 1e-3f;
+        s = cbrtf(fmaxf(ext[0], fl) * fmaxf(ext[1], fl) * fmaxf(ext[2], fl) / (float)cells_cap);
+    }
+    if (!(s > emax * 1e-6f)) s = emax;          // absurdly small cell: a single cell
+    if (!(s > 0.f)) s = 1.f;
+    int n[3];
+    for (int it = 0; it < 256; ++it) {
+        double prod = 1.0;
+        for (int d = 0; d < 3; ++d) {
+            float c = floorf(ext[d] / s) + 1.f;
+            n[d] = (c < 1.f) ? 1 : (c > 1.0e6f ? 1000000 : (int)c);
+            prod *= (double)n[d];
+        }
+        if (prod <= (double)cells_cap) break;
+        s *= 1.26f;
+        if (it == 255) { n[0] = n[1] = n[2] = 1; s = emax; }
+    }
+    h.ox = lo[0]; h.oy = lo[1]; h.oz = lo[2];
+    h.hx = hi[0]; h.hy = hi[1]; h.hz = hi[2];
+    h.s = s; h.inv_s = 1.0f / s;
+    h.nx = n[0]; h.ny = n[1]; h.nz = n[2];
+    h.ncells = n[0] * n[1] * n[2];
+    h.n_sorted = 0;
+    h.pad[0] = h.pad[1] = h.pad[2] = 0;
+    hdr[b] = h;
+}
+
+UME_DEVI bool point_cell(const GridHeader& h, float x, float y, float z, int* cell) {
+    bool inside = (x >= h.ox) && (x <= h.hx) && (y >= h.oy) && (y <= h.hy) && (z >= h.oz) && (z <= h.hz);
+    if (!inside) return false;
+    int cx = cell_coord(x, h.ox, h.inv_s, h.nx);
+    int cy = cell_coord(y, h.oy, h.inv_s, h.ny);
+    int cz = cell_coord(z, h.oz, h.inv_s, h.nz);
+    *cell = (cz * h.ny + cy) * h.nx + cx;
+    return true;
+}
+
+// pass 0: count, pass 1: scatter.  grid = (chunks, B)
+template <int kPass>
+__global__ void grid_bin_kernel(const float* __restrict__ pts, int N, const GridHeader* __restrict__ hdr,
+                                int* __restrict__ cursor, int cells_cap, float4* __restrict__ sorted) {
+    const int b = blockIdx.y;
+    const GridHeader h = hdr[b];
+    const float* pb = pts + (size_t)b * N * 3;
+    int* cur = cursor + (size_t)b * cells_cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        float x = pb[i * 3 + 0], y = pb[i * 3 + 1], z = pb[i * 3 + 2];
+        int cell;
+        if (point_cell(h, x, y, z, &cell)) {
+            if (kPass == 0) {
+                atomicAdd(&cur[cell], 1);
+            } else {
+                int pos = atomicAdd(&cur[cell], 1);
+                sorted[(size_t)b * N + pos] = make_float4(x, y, z, __int_as_float(i));
+            }
+        }
+    }
+}
+
+// One CTA per cloud: exclusive scan of the per-cell counts.  cursor[] becomes the running write
+// position of each cell, cell_start[] the immutable start offsets (cells_cap + 1 entries).
+__global__ void __launch_bounds__(1024) grid_scan_kernel(int* __restrict__ cursor, int* __restrict__ cell_start,
+                                                         GridHeader* __restrict__ hdr, int cells_cap) {
+    const int b = blockIdx.x;
+    int* cur = cursor + (size_t)b * cells_cap;
+    int* cs = cell_start + (size_t)b * (cells_cap + 1);
+    const int per = (cells_cap + 1023) / 1024;
+    const int t = threadIdx.x;
+    const int lo = t * per, hi = min(lo + per, cells_cap);
+    int sum = 0;
+    for (int c = lo; c < hi; ++c) sum += cur[c];
+    // block exclusive scan of `sum`
+    __shared__ int warp_tot[32];
+    const int lane = t & 31, w = t >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(UME_FULL_MASK, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int v = warp_tot[lane];
+        int iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(UME_FULL_MASK, iv, o);
+            if (lane >= o) iv += u;
+        }
+        warp_tot[lane] = iv - v;   // exclusive
+    }
+    __syncthreads();
+    int run = warp_tot[w] + incl - sum;
+    for (int c = lo; c < hi; ++c) {
+        int v = cur[c];
+        cs[c] = run;
+        cur[c] = run;
+        run += v;
+    }
+    if (t == 1023) {
+        cs[cells_cap] = run;
+        hdr[b].n_sorted = run;
+    }
+}
+
+}  // namespace
+
+size_t grid_workspace_bytes(int B, int N, int cells_cap) {
+    size_t s = 0;
+    s = align_up(s, 256) + (size_t)B * sizeof(GridHeader);
+    s = align_up(s, 256) + (size_t)B * 6 * sizeof(int);
+    s = align_up(s, 256) + (size_t)B * cells_cap * sizeof(int);
+    s = align_up(s, 256) + (size_t)B * (cells_cap + 1) * sizeof(int);
+    s = align_up(s, 256) + (size_t)B * N * sizeof(float4);
+    return align_up(s, 256);
+}
+
+int grid_build(const float* pts, const float* q, int B, int N, int nq, float expand, float cell,
+               int cells_cap, Workspace& ws, GridView* view, cudaStream_t stream) {
+    GridHeader* hdr = ws.take<GridHeader>(B);
+    int* bbox = ws.take<int>((size_t)B * 6);
+    int* cursor = ws.take<int>((size_t)B * cells_cap);
+    int* cell_start = ws.take<int>((size_t)B * (cells_cap + 1));
+    float4* sorted = ws.take<float4>((size_t)B * N);
+    UME_REQUIRE(ws.ok(), UME_ERR_WORKSPACE, "grid_build: workspace too small (%zu needed, %zu given)",
+                ws.used, ws.size);
+
+    grid_init_kernel<<<(B * 6 + 127) / 128, 128, 0, stream>>>(bbox, B);
+    if (nq > 0) {
+        dim3 g((unsigned)min((nq + 255) / 256, 64), (unsigned)B);
+        grid_bbox_kernel<<<g, 256, 0, stream>>>(q, nq, bbox);
+    }
+    grid_params_kernel<<<(B + 127) / 128, 128, 0, stream>>>(bbox, hdr, B, expand, cell, cells_cap);
+    cudaMemsetAsync(cursor, 0, (size_t)B * cells_cap * sizeof(int), stream);
+    dim3 gb((unsigned)min((N + 255) / 256, 296), (unsigned)B);
+    grid_bin_kernel<0><<<gb, 256, 0, stream>>>(pts, N, hdr, cursor, cells_cap, sorted);
+    grid_scan_kernel<<<B, 1024, 0, stream>>>(cursor, cell_start, hdr, cells_cap);
+    grid_bin_kernel<1><<<gb, 256, 0, stream>>>(pts, N, hdr, cursor, cells_cap, sorted);
+    count_launch(nq > 0 ? 7 : 6);
+    view->hdr = hdr;
+    view->cell_start = cell_start;
+    view->sorted = sorted;
+    view->cells_cap = cells_cap;
+    view->N = N;
+    return check_launch("grid_build");
+}
+
+}  // namespace ume

@@ -1,0 +1,260 @@
+// Fused radius-neighbourhood gather + UME moment build (replaces evaluate.py:50-60).
+//
+// One CTA per keypoint.  The neighbourhood is collected into shared memory as (point - keypoint,
+// row index) entries (neighbors.cuh); the gather then streams the neighbours' feature rows from
+// HBM/L2 with 128-bit loads — a C=32 row is exactly one 128-byte line, 8 lanes x float4 — and
+// accumulates the C x 4 matrix [sum f | sum f (x-k)^T] in registers.  Partial sums are combined
+// with warp shuffles and one shared-memory pass, un-centred (F1 = F1c + k F0), normalised as the
+// reference does and written as one 16-byte row per channel.  The (B,n,K,C) gather tensor the
+// reference materialises (evaluate.py:54-55) never exists.
+#include "neighbors.cuh"
+
+namespace ume {
+
+namespace {
+
+constexpr int kNT = 256;
+constexpr int kNW = kNT / 32;
+
+struct MomentsParams {
+    GridView grid;
+    const float* kpts;    // (B,n,3)
+    const float* feat;    // (B,N,C)
+    float* F;             // (B,n,C,4)
+    float* Fc;            // (B,n,C,4) or null
+    int32_t* count;       // (B,n) or null
+    int n, C, K, cap;
+    float radius;
+};
+
+// ---- accumulators: vectorised (C = 4*LPR, LPR lanes x float4 per feature row) ----------------
+template <int LPR>
+struct VecAcc {
+    static constexpr int C = 4 * LPR;
+    static constexpr int RPW = 32 / LPR;       // feature rows per warp instruction
+    float a[4][4];                             // [channel within lane][moment 1,x,y,z]
+
+    UME_DEVI void set_channels(int) {}
+    UME_DEVI void clear() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
+    }
+    UME_DEVI void add(const float4& nb, const float4& f) {
+        const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i][0] += fv[i];
+            a[i][1] = fmaf(fv[i], nb.x, a[i][1]);
+            a[i][2] = fmaf(fv[i], nb.y, a[i][2]);
+            a[i][3] = fmaf(fv[i], nb.z, a[i][3]);
+        }
+    }
+    UME_DEVI void gather(const float4* list, int len, const float* __restrict__ feat_b) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int sub = lane / LPR, l = lane % LPR;
+        constexpr int stride = kNW * RPW;
+        const float* fl = feat_b + 4 * l;
+        int e = warp * RPW + sub;
+        for (; e + 3 * stride < len; e += 4 * stride) {
+            float4 nb[4], f[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nb[u] = list[e + u * stride];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) f[u] = ldg_f4(fl + (size_t)__float_as_int(nb[u].w) * C);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) add(nb[u], f[u]);
+        }
+        for (; e < len; e += stride) {
+            const float4 nb = list[e];
+            add(nb, ldg_f4(fl + (size_t)__float_as_int(nb.w) * C));
+        }
+    }
+    // combine the RPW row groups of the warp, then lanes [0,LPR) hold the warp's C x 4 partial
+    UME_DEVI void store(float4* red_w) {
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a[i][j] += __shfl_xor_sync(UME_FULL_MASK, a[i][j], o);
+        const int lane = threadIdx.x & 31;
+        if (lane < LPR) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) red_w[4 * lane + i] = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
+        }
+    }
+};
+
+// ---- accumulators: any C <= 32*CJ, one feature row per warp instruction, scalar loads --------
+template <int CJ>
+struct GenAcc {
+    float a[CJ][4];
+    int C;
+    UME_DEVI void set_channels(int c) { C = c; }
+    UME_DEVI void clear() {
+#pragma unroll
+        for (int i = 0; i < CJ; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
+    }
+    UME_DEVI void add_row(const float4& nb, const float* __restrict__ row) {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int i = 0; i < CJ; ++i) {
+            const int c = lane + 32 * i;
+            const float f = (c < C) ? __ldg(row + c) : 0.f;
+            a[i][0] += f;
+            a[i][1] = fmaf(f, nb.x, a[i][1]);
+            a[i][2] = fmaf(f, nb.y, a[i][2]);
+            a[i][3] = fmaf(f, nb.z, a[i][3]);
+        }
+    }
+    UME_DEVI void gather(const float4* list, int len, const float* __restrict__ feat_b) {
+        const int warp = threadIdx.x >> 5;
+        int e = warp;
+        for (; e + kNW < len; e += 2 * kNW) {
+            const float4 n0 = list[e], n1 = list[e + kNW];
+            add_row(n0, feat_b + (size_t)__float_as_int(n0.w) * C);
+            add_row(n1, feat_b + (size_t)__float_as_int(n1.w) * C);
+        }
+        for (; e < len; e += kNW) {
+            const float4 n0 = list[e];
+            add_row(n0, feat_b + (size_t)__float_as_int(n0.w) * C);
+        }
+    }
+    UME_DEVI void store(float4* red_w) {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int i = 0; i < CJ; ++i) {
+            const int c = lane + 32 * i;
+            if (c < C) red_w[c] = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
+        }
+    }
+};
+
+template <typename Acc, bool kFma>
+__global__ void __launch_bounds__(kNT) moments_kernel(MomentsParams p) {
+    extern __shared__ float4 list[];            // cap entries; reused as reduction scratch
+    __shared__ CollectSmem sm;
+    __shared__ float s_f0[256];
+
+    const int q = blockIdx.x;
+    const int b = q / p.n;
+    const int C = p.C;
+    const GridHeader h = p.grid.hdr[b];
+    const int* cs = p.grid.cell_start + (size_t)b * (p.grid.cells_cap + 1);
+    const float4* sorted_b = p.grid.sorted + (size_t)b * p.grid.N;
+    const float* feat_b = p.feat + (size_t)b * p.grid.N * C;
+    const float kx = p.kpts[(size_t)q * 3 + 0], ky = p.kpts[(size_t)q * 3 + 1], kz = p.kpts[(size_t)q * 3 + 2];
+
+    Acc acc;
+    acc.clear();
+    acc.set_channels(C);
+
+    const int used = collect_neighbors<kFma, kNT>(
+        sm, list, p.cap, h, cs, sorted_b, p.grid.N, kx, ky, kz, p.radius, p.K, [&](int len) {
+            __syncthreads();                     // list entries of every warp are visible
+            acc.gather(list, len, feat_b);
+        });
+
+    __syncthreads();                             // everyone is done reading the list
+    const int warp = threadIdx.x >> 5;
+    acc.store(list + (size_t)warp * C);
+    __syncthreads();
+    const int c = threadIdx.x;
+    float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+#pragma unroll
+        for (int w = 0; w < kNW; ++w) {
+            const float4 v = list[(size_t)w * C + c];
+            row.x += v.x; row.y += v.y; row.z += v.z; row.w += v.w;
+        }
+        s_f0[c] = row.x;
+    }
+    __syncthreads();
+    if (c < C) {
+        float s = 0.f;
+        for (int i = 0; i < C; ++i) s += s_f0[i];          // same order in every thread
+        const float den = s + 1e-6f;                        // evaluate.py:59
+        const size_t o = ((size_t)q * C + c) * 4;
+        float4 out;
+        out.x = row.x / den;
+        out.y = (row.y + kx * row.x) / den;                // un-centre: sum f x = sum f (x-k) + k sum f
+        out.z = (row.z + ky * row.x) / den;
+        out.w = (row.w + kz * row.x) / den;
+        *reinterpret_cast<float4*>(p.F + o) = out;
+        if (p.Fc) *reinterpret_cast<float4*>(p.Fc + o) = make_float4(row.x / den, row.y / den, row.z / den, row.w / den);
+    }
+    if (threadIdx.x == 0 && p.count) p.count[q] = used;
+}
+
+template <typename Acc>
+int launch_moments(const MomentsParams& p, int B, bool fma, cudaStream_t stream) {
+    const size_t smem = (size_t)p.cap * sizeof(float4);
+    auto kern = fma ? moments_kernel<Acc, true> : moments_kernel<Acc, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    UME_REQUIRE(e == cudaSuccess, UME_ERR_CUDA, "moments: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    kern<<<(unsigned)((size_t)B * p.n), kNT, smem, stream>>>(p);
+    count_launch();
+    return check_launch("moments_kernel");
+}
+
+}  // namespace
+
+static int moments_cap(int C, int K) {
+    (void)K;
+    int cap = 2048;
+    while (cap < kNW * C) cap *= 2;              // reduction scratch must fit in the list
+    return cap;
+}
+
+}  // namespace ume
+
+extern "C" size_t ume_moments_workspace_bytes(int B, int N, int n, int C, int K) {
+    (void)n; (void)C; (void)K;
+    if (B <= 0 || N <= 0) return 0;
+    return ume::grid_workspace_bytes(B, N, ume::kCellsCap) + 256;
+}
+
+extern "C" int ume_moments_f32(const float* pts, const float* kpts, const float* feat, int B, int N, int n,
+                               int C, int K, float radius, unsigned flags, float* F, float* Fc,
+                               int32_t* count, void* ws, size_t ws_bytes, void* stream_) {
+    using namespace ume;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    UME_REQUIRE(B >= 0 && N >= 0 && n >= 0, UME_ERR_BAD_ARG, "ume_moments_f32: negative size");
+    if (B == 0 || n == 0) return UME_OK;
+    UME_REQUIRE(pts && kpts && feat && F, UME_ERR_BAD_ARG, "ume_moments_f32: null pointer");
+    UME_REQUIRE(N >= 1, UME_ERR_BAD_ARG, "ume_moments_f32: empty cloud (N = 0)");
+    UME_REQUIRE(C >= 1 && C <= 256, UME_ERR_UNSUPPORTED, "ume_moments_f32: C = %d not in [1,256]", C);
+    UME_REQUIRE(K >= 1, UME_ERR_BAD_ARG, "ume_moments_f32: K = %d < 1", K);
+    UME_REQUIRE(N <= kMaxPoints, UME_ERR_UNSUPPORTED, "ume_moments_f32: N = %d > %d", N, kMaxPoints);
+    UME_REQUIRE((size_t)B * n < 0x7fffffffull, UME_ERR_UNSUPPORTED, "ume_moments_f32: B*n too large");
+    UME_REQUIRE(ws && ws_bytes >= ume_moments_workspace_bytes(B, N, n, C, K), UME_ERR_WORKSPACE,
+                "ume_moments_f32: workspace too small (%zu needed, %zu given)",
+                ume_moments_workspace_bytes(B, N, n, C, K), ws_bytes);
+    Workspace w(ws, ws_bytes);
+    MomentsParams p;
+    int rc = grid_build(pts, kpts, B, N, n, fabsf(radius), fabsf(radius) / ((flags & UME_FLAG_CELL_DIV2) ? 2.f : 1.f), kCellsCap, w, &p.grid, stream);
+    if (rc != UME_OK) return rc;
+    p.kpts = kpts; p.feat = feat; p.F = F; p.Fc = Fc; p.count = count;
+    p.n = n; p.C = C; p.K = K; p.cap = moments_cap(C, K); p.radius = radius;
+    const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
+    const bool vec = (C % 4 == 0) && ((C & (C - 1)) == 0) && C >= 4 && C <= 128 &&
+                     (reinterpret_cast<uintptr_t>(feat) % 16 == 0);
+    if (vec) {
+        switch (C) {
+            case 4: return launch_moments<VecAcc<1>>(p, B, fma, stream);
+            case 8: return launch_moments<VecAcc<2>>(p, B, fma, stream);
+            case 16: return launch_moments<VecAcc<4>>(p, B, fma, stream);
+            case 32: return launch_moments<VecAcc<8>>(p, B, fma, stream);
+            case 64: return launch_moments<VecAcc<16>>(p, B, fma, stream);
+            default: return launch_moments<VecAcc<32>>(p, B, fma, stream);
+        }
+    }
+    if (C <= 32) return launch_moments<GenAcc<1>>(p, B, fma, stream);
+    if (C <= 64) return launch_moments<GenAcc<2>>(p, B, fma, stream);
+    if (C <= 128) return launch_moments<GenAcc<4>>(p, B, fma, stream);
+    return launch_moments<GenAcc<8>>(p, B, fma, stream);
+}

@@ -1,0 +1,302 @@
+// CTA-level neighbourhood collection shared by the ball-query and the fused moment kernels.
+//
+// One CTA serves one query.  Candidates come from the search grid (contiguous runs of the
+// cell-sorted point array, one run per (y,z) cell row); membership is decided by the exact fp32
+// distance test; "the first K rows in row order" (pytorch3d ball_query semantics, evaluate.py:51)
+// is recovered WITHOUT scanning in row order: the K smallest row indices among the in-radius
+// candidates are found with a two-level counting select (histogram over index bins, then a bitmap
+// inside the crossing bin), which works for any number of hits.
+#pragma once
+#include "ume_common.cuh"
+
+namespace ume {
+
+static constexpr int kMaxRows = 64;       // (2*div+2)^2 <= 36 cell rows per query
+static constexpr int kHistBins = 2048;
+static constexpr int kBitmapWords = 128;  // bin width <= 4096 indices  ->  N <= 2048*4096
+
+struct CollectSmem {
+    int seg_start[kMaxRows];
+    int seg_prefix[kMaxRows + 1];
+    unsigned hist[kHistBins];
+    unsigned bitmap[kBitmapWords];
+    int warp_cnt[32];
+    int count;        // hits appended so far (may exceed the list capacity)
+    int sel_bin, sel_below, sel_T;
+    int nrows, total;
+};
+
+// ---------------------------------------------------------------- phase 0: candidate runs
+template <int NT>
+UME_DEVI void collect_rows(CollectSmem& sm, const GridHeader& h, const int* __restrict__ cs, float kx,
+                           float ky, float kz, float radius) {
+    const float r = fabsf(radius);
+    const float mx = r * 1e-4f + fabsf(kx) * 1e-6f + 1e-7f;
+    const float my = r * 1e-4f + fabsf(ky) * 1e-6f + 1e-7f;
+    const float mz = r * 1e-4f + fabsf(kz) * 1e-6f + 1e-7f;
+    const int cx0 = cell_coord(kx - r - mx, h.ox, h.inv_s, h.nx);
+    const int cx1 = cell_coord(kx + r + mx, h.ox, h.inv_s, h.nx);
+    const int cy0 = cell_coord(ky - r - my, h.oy, h.inv_s, h.ny);
+    const int cy1 = cell_coord(ky + r + my, h.oy, h.inv_s, h.ny);
+    const int cz0 = cell_coord(kz - r - mz, h.oz, h.inv_s, h.nz);
+    const int cz1 = cell_coord(kz + r + mz, h.oz, h.inv_s, h.nz);
+    const int nyr = cy1 - cy0 + 1, nzr = cz1 - cz0 + 1;
+    int nrows = nyr * nzr;
+    if (nrows > kMaxRows) nrows = kMaxRows;     // cannot happen: cell >= radius/2 (see grid_params_kernel)
+    const float rr = (r + 4.f * (mx + my + mz));
+    const float rr2 = rr * rr;
+    for (int row = threadIdx.x; row < nrows; row += NT) {
+        const int iy = cy0 + row % nyr, iz = cz0 + row / nyr;
+        // prune rows / trim the x range by the distance from the query to the cell slab; the
+        // outermost cells also hold clamped coordinates, so they are treated as unbounded
+        float dy = 0.f, dz = 0.f;
+        {
+            float lo = h.oy + (float)iy * h.s, hi = lo + h.s;
+            if (iy > 0 && ky < lo) dy = lo - ky;
+            if (iy < h.ny - 1 && ky > hi) dy = ky - hi;
+            lo = h.oz + (float)iz * h.s; hi = lo + h.s;
+            if (iz > 0 && kz < lo) dz = lo - kz;
+            if (iz < h.nz - 1 && kz > hi) dz = kz - hi;
+        }
+        const float rem2 = rr2 - dy * dy - dz * dz;
+        int s = 0, n = 0;
+        if (rem2 > 0.f) {
+            const float half = sqrtf(rem2) * 1.0001f + mx;
+            const int tx0 = max(cx0, cell_coord(kx - half, h.ox, h.inv_s, h.nx));
+            const int tx1 = min(cx1, cell_coord(kx + half, h.ox, h.inv_s, h.nx));
+            if (tx1 >= tx0) {
+                const int base = (iz * h.ny + iy) * h.nx;
+                s = cs[base + tx0];
+                n = cs[base + tx1 + 1] - s;
+            }
+        }
+        sm.seg_start[row] = s;
+        sm.seg_prefix[row + 1] = n;       // lengths for now; prefix-summed below
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        sm.seg_prefix[0] = 0;
+        for (int r_ = 0; r_ < nrows; ++r_) {
+            run += sm.seg_prefix[r_ + 1];
+            sm.seg_prefix[r_ + 1] = run;
+        }
+        sm.nrows = nrows;
+        sm.total = run;
+        sm.count = 0;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- candidate walk
+// visit(hit, ex, ey, ez, d2, row_index) is called by ALL threads of the CTA the same number of
+// times (so it may use warp votes and __syncthreads); e = point - query.
+template <bool kFma, int NT, typename Visit>
+UME_DEVI void scan_candidates(const CollectSmem& sm, const float4* __restrict__ sorted_b, float kx, float ky,
+                              float kz, float r2, Visit visit) {
+    const int total = sm.total;
+    int seg = 0;
+    for (int base = 0; base < total; base += NT) {
+        const int j = base + threadIdx.x;
+        const bool valid = j < total;
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            while (j >= sm.seg_prefix[seg + 1]) ++seg;
+            c = __ldg(&sorted_b[sm.seg_start[seg] + (j - sm.seg_prefix[seg])]);
+        }
+        const float ex = __fsub_rn(c.x, kx), ey = __fsub_rn(c.y, ky), ez = __fsub_rn(c.z, kz);
+        const float d2 = dist2_ordered<kFma>(ex, ey, ez);
+        visit(valid && (d2 < r2), ex, ey, ez, d2, __float_as_int(c.w));
+    }
+}
+
+// Warp-aggregated append of hits to list[0..cap); sm.count keeps counting past cap.
+UME_DEVI void append_hit(CollectSmem& sm, float4* list, int cap, bool hit, float ex, float ey, float ez, int idx) {
+    const unsigned m = __ballot_sync(UME_FULL_MASK, hit);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(m) - 1;
+        int basepos = 0;
+        if (lane == leader) basepos = atomicAdd(&sm.count, __popc(m));
+        basepos = __shfl_sync(UME_FULL_MASK, basepos, leader);
+        if (hit) {
+            const int pos = basepos + __popc(m & lanemask_lt());
+            if (pos < cap) list[pos] = make_float4(ex, ey, ez, __int_as_float(idx));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- counting select
+// Given that more than K candidates are in radius, find T = the K-th smallest row index among
+// them.  `each(f)` must call f(row_index) once per in-radius candidate (any thread, any order).
+template <int NT, typename Each>
+UME_DEVI int select_kth_index(CollectSmem& sm, int K, int shift, Each each) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kHistBins; i += NT) sm.hist[i] = 0;
+    __syncthreads();
+    each([&](int idx) { atomicAdd(&sm.hist[idx >> shift], 1u); });
+    __syncthreads();
+    {
+        constexpr int per = kHistBins / NT;
+        const int lo = tid * per;
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < per; ++i) s += (int)sm.hist[lo + i];
+        int incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(UME_FULL_MASK, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) sm.warp_cnt[warp] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += sm.warp_cnt[w];
+        const int excl = wbase + incl - s;
+        if (excl < K && K <= excl + s) {
+            int run = excl;
+            for (int i = 0; i < per; ++i) {
+                const int hcount = (int)sm.hist[lo + i];
+                if (run + hcount >= K) {
+                    sm.sel_bin = lo + i;
+                    sm.sel_below = run;
+                    break;
+                }
+                run += hcount;
+            }
+        }
+    }
+    for (int i = tid; i < kBitmapWords; i += NT) sm.bitmap[i] = 0;
+    __syncthreads();
+    const int bin = sm.sel_bin;
+    const int need = K - sm.sel_below;                 // >= 1 indices wanted from the crossing bin
+    const unsigned wmask = (1u << shift) - 1u;
+    each([&](int idx) {
+        if ((idx >> shift) == bin) {
+            const unsigned off = (unsigned)idx & wmask;
+            atomicOr(&sm.bitmap[off >> 5], 1u << (off & 31));
+        }
+    });
+    __syncthreads();
+    if (warp == 0) {
+        int run = 0;
+        bool done = false;
+        for (int t = 0; t < kBitmapWords / 32 && !done; ++t) {
+            const unsigned word = sm.bitmap[t * 32 + lane];
+            const int pc = __popc(word);
+            int incl = pc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(UME_FULL_MASK, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int excl = run + incl - pc;
+            const bool mine = (excl < need) && (need <= excl + pc);
+            if (mine) {
+                unsigned wd = word;
+                for (int k = need - excl; k > 1; --k) wd &= wd - 1;   // drop the k-1 lowest set bits
+                const int bit = __ffs(wd) - 1;
+                sm.sel_T = (bin << shift) + (t * 32 + lane) * 32 + bit;
+            }
+            done = __any_sync(UME_FULL_MASK, mine);
+            run += __shfl_sync(UME_FULL_MASK, incl, 31);
+        }
+    }
+    __syncthreads();
+    return sm.sel_T;
+}
+
+// In-place stable-free compaction of list[0..count): keep entries whose row index <= T.
+template <int NT>
+UME_DEVI int compact_list(CollectSmem& sm, float4* list, int count, int T) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    int out = 0;
+    for (int base = 0; base < count; base += NT) {
+        const int i = base + tid;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool keep = false;
+        if (i < count) {
+            v = list[i];
+            keep = __float_as_int(v.w) <= T;
+        }
+        const unsigned m = __ballot_sync(UME_FULL_MASK, keep);
+        if (lane == 0) sm.warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int wbase = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const int c = sm.warp_cnt[w];
+            if (w < warp) wbase += c;
+            tot += c;
+        }
+        if (keep) list[out + wbase + __popc(m & lanemask_lt())] = v;
+        out += tot;
+        __syncthreads();
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------- driver
+// Collects the neighbourhood of one query and hands it to `flush(len)` as a dense list of
+// (ex, ey, ez, row index) entries, at most `cap` at a time (`flush` is called once unless the hits
+// overflow the list AND K > cap).  Returns the number of neighbours = min(K, #in radius).
+template <bool kFma, int NT, typename Flush>
+UME_DEVI int collect_neighbors(CollectSmem& sm, float4* list, int cap, const GridHeader& h,
+                               const int* __restrict__ cs, const float4* __restrict__ sorted_b, int N, float kx,
+                               float ky, float kz, float radius, int K, Flush flush) {
+    const float r2 = __fmul_rn(radius, radius);
+    collect_rows<NT>(sm, h, cs, kx, ky, kz, radius);
+    scan_candidates<kFma, NT>(sm, sorted_b, kx, ky, kz, r2,
+                              [&](bool hit, float ex, float ey, float ez, float, int idx) {
+                                  append_hit(sm, list, cap, hit, ex, ey, ez, idx);
+                              });
+    __syncthreads();
+    const int count = sm.count;
+    int shift = 0;
+    while (((N - 1) >> shift) >= kHistBins) ++shift;
+    if (count <= cap) {
+        int len = count;
+        if (count > K) {
+            const int T = select_kth_index<NT>(sm, K, shift, [&](auto f) {
+                for (int i = threadIdx.x; i < count; i += NT) f(__float_as_int(list[i].w));
+            });
+            len = compact_list<NT>(sm, list, count, T);
+        }
+        flush(len);
+        return len;
+    }
+    // Overflow: more hits than the list holds.  Everything is recomputed from the candidates.
+    int T = 0x7fffffff;
+    if (count > K) {
+        T = select_kth_index<NT>(sm, K, shift, [&](auto f) {
+            scan_candidates<kFma, NT>(sm, sorted_b, kx, ky, kz, r2,
+                                      [&](bool hit, float, float, float, float, int idx) {
+                                          if (hit) f(idx);
+                                      });
+        });
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sm.count = 0;
+    __syncthreads();
+    int len = 0;   // block-uniform running length of the list (sm.count only hands out slots)
+    scan_candidates<kFma, NT>(sm, sorted_b, kx, ky, kz, r2,
+                              [&](bool hit, float ex, float ey, float ez, float, int idx) {
+                                  const bool acc = hit && idx <= T;
+                                  const int n_acc = __syncthreads_count(acc);   // also orders the appends
+                                  if (len + n_acc > cap) {
+                                      flush(len);
+                                      __syncthreads();
+                                      if (threadIdx.x == 0) sm.count = 0;
+                                      __syncthreads();
+                                      len = 0;
+                                  }
+                                  append_hit(sm, list, cap, acc, ex, ey, ez, idx);
+                                  len += n_acc;
+                              });
+    __syncthreads();
+    flush(len);
+    return count > K ? K : count;
+}
+
+}  // namespace ume
