@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Throughput of the UME descriptor-and-registration hot path (BASELINE.json metric: pairs/sec,
+KITTI-shape pairs, 1024 keypoints) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] ...                  # the CPU reference arm
+
+A step = one pass of the hot path (evaluate.py:206-257: UME matrices of both clouds, all-pairs
+subspace distance + arg-min, one rigid hypothesis per match) over one batch of synthetic
+KITTI-shape pairs (BASELINE config #3: 64 pairs x ~120k points, 1024 keypoints, 32 channels,
+K = 750, r = 5 m).  With N > 1 every rank owns its own 64 pairs (weak scaling, no data-path
+collective) and the step ends with one NCCL all-gather of the per-pair results.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: pairs per GPU, points, keypoints, channels, lidar model
+    "kitti_b64_n1024_c32": dict(pairs=64, N=120000, n_kp=1024, C=32, model="KITTI"),
+    "kitti_b1_n512_c32": dict(pairs=1, N=120000, n_kp=512, C=32, model="KITTI"),
+    "nuscenes_b64_n1024_c32": dict(pairs=64, N=35000, n_kp=1024, C=32, model="NUSCENES"),
+    "rotkitti_b32_n2048_c64": dict(pairs=32, N=120000, n_kp=2048, C=64, model="KITTI"),
+    "tiny": dict(pairs=4, N=20000, n_kp=256, C=32, model="KITTI"),
+}
+K_NN, RADIUS = 750, 5.0
+METRIC, UNIT = "pairs_per_sec_kitti_shape_1024kp", "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="kitti_b64_n1024_c32", choices=sorted(WORKLOADS))
+    ap.add_argument("--cdist-impl", type=int, default=None, help="0 = SIMT fp32, 1 = tcgen05")
+    ap.add_argument("--cell-div2", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-pairs", type=int, default=24)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def make_workload(wl, seed0):
+    from umeregrobust_b200 import synth
+    model = getattr(synth, wl["model"])
+    return synth.make_batch(wl["pairs"], seed0=seed0, n_base=min(4, wl["pairs"]), N=wl["N"], C=wl["C"],
+                            n_kp=wl["n_kp"], model=model)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+                for nm, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU reference leg
+def cpu_reference_pairs(batch, idxs, threads):
+    """The oracle's port of evaluate.py:206-257 (fp32, all host threads) on pairs `idxs`."""
+    from oracle import ume_oracle as orc
+    from oracle import pytorch3d_ops as p3d
+    p3d._load()
+    t0 = time.perf_counter()
+    for p in idxs:
+        orc.register_pair_hypotheses(batch["src_pts"][p:p + 1], batch["src_feat"][p:p + 1], batch["src_kp"][p:p + 1],
+                                     batch["tgt_pts"][p:p + 1], batch["tgt_feat"][p:p + 1], batch["tgt_kp"][p:p + 1],
+                                     K_NN, RADIUS, dtype=np.float32)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's algorithm on the host cores (oracle port: numpy + the C
+    restatement of pytorch3d.ball_query with OpenMP; the reference itself is Python on top of
+    wheels that cannot be installed offline).  One step = ONE pair of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pytorch3d_ops as p3d
+    threads = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    small = dict(wl, pairs=min(wl["pairs"], 2))
+    batch = make_workload(small, seed0=0)
+    for w in range(args.warmup):
+        cpu_reference_pairs(batch, [w % small["pairs"]], threads)
+        if w >= 0:
+            break                                   # one warm-up pair is enough for a CPU path (page-in, OpenMP pool)
+    times = [cpu_reference_pairs(batch, [s % small["pairs"]], threads) for s in range(args.steps)]
+    per_step = float(np.mean(times))
+    value = 1.0 / per_step
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": per_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "pairs_per_step": 1, "points": wl["N"], "keypoints": wl["n_kp"],
+                       "channels": wl["C"], "K": K_NN, "radius": RADIUS},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": p3d.c_num_threads(), "kind": "port",
+                             "sample": "1 pair of the workload per step (oracle port: numpy + OpenMP C ball_query)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- CUDA arm
+def algorithmic_bytes(counts, n_kp, C):
+    """per cloud  sum_i cnt_i (4C + 12) + n (12 + 16C)."""
+    return float(counts.sum()) * (4 * C + 12) + counts.shape[0] * n_kp * (12 + 16 * C)
+
+
+def run_b200(args, wl):
+    import torch
+    import torch.distributed as dist
+    import umeregrobust_b200 as ume
+    from umeregrobust_b200 import _lib
+    from umeregrobust_b200.engine import RegistrationEngine, gather_results
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", local if world > 1 else 0)
+    _lib.lib()
+    if args.cdist_impl is not None:
+        ume.config["cdist_impl"] = args.cdist_impl
+    if args.cell_div2 is not None:
+        ume.config["cell_div2"] = bool(args.cell_div2)
+
+    batch_np = make_workload(wl, seed0=10000 * rank)
+    keys = ("src_pts", "src_feat", "src_kp", "tgt_pts", "tgt_feat", "tgt_kp")
+    batch = {k: torch.from_numpy(batch_np[k]).to(dev) for k in keys}
+    eng = RegistrationEngine(K=K_NN, radius=RADIUS, device=dev, want_D=True)
+    pairs = wl["pairs"]
+
+    def step():
+        out = eng.register(batch)
+        if world > 1:
+            out = gather_results(out)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # neighbour counts (outside the timed region) -> algorithmic bytes of the gather+moment kernel
+    _, cnt_s = ume.ume_moments(batch["src_pts"], batch["src_kp"], batch["src_feat"], K_NN, RADIUS, return_count=True)
+    _, cnt_t = ume.ume_moments(batch["tgt_pts"], batch["tgt_kp"], batch["tgt_feat"], K_NN, RADIUS, return_count=True)
+    cnt_s, cnt_t = cnt_s.cpu().numpy(), cnt_t.cpu().numpy()
+    bytes_per_launch = 0.5 * (algorithmic_bytes(cnt_s, wl["n_kp"], wl["C"]) + algorithmic_bytes(cnt_t, wl["n_kp"], wl["C"]))
+
+    sampler = ClockSampler(local if world > 1 else 0)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    _lib.profile_reset()
+    _lib.profile_enable(True)
+    barrier()
+    launches0 = _lib.launch_count()
+    t_host0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    t_host1 = time.time()
+    launches = _lib.launch_count() - launches0
+    _lib.profile_enable(False)
+    prof = _lib.profile_read()
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    clocks = sampler.stop(t_host0, t_host1) if rank == 0 else None
+    ms_per_step = elapsed_ms / args.steps
+    value = world * pairs / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    host = {k: torch.from_numpy(batch_np[k]).pin_memory() for k in keys}
+    h2d, d2h = RegistrationEngine.host_bytes(host)
+    for _ in range(2):
+        eng.register_host(host)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.e2e_steps):
+        res = eng.register_host(host)
+        if world > 1:
+            gather_results({k: v.to(dev, non_blocking=True) for k, v in res.items()})
+    s1.record()
+    barrier()
+    e2e_ms = s0.elapsed_time(s1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * pairs / (e2e_ms / args.e2e_steps * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    peaks_note = "fallback"
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        peaks_note = "measured"
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    mom_ms, mom_n = prof["moments"]
+    mom_avg_ms = mom_ms / max(mom_n, 1)
+    achieved = bytes_per_launch / (mom_avg_ms * 1e-3) / 1e9 if mom_n else None
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(REPO, "profiles", "moments_dram_traffic.json")))
+        if tr.get("workload") == args.workload:
+            traffic = tr.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    stages = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+              for k, v in prof.items() if v[1]}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "pairs_per_gpu_per_step": pairs, "points": wl["N"],
+                   "keypoints": wl["n_kp"], "channels": wl["C"], "K": K_NN, "radius": RADIUS,
+                   "mean_neighbours": float(0.5 * (cnt_s.mean() + cnt_t.mean())),
+                   "cdist_impl": ume.config["cdist_impl"], "cell_div2": ume.config["cell_div2"],
+                   "l2_policy": "inputs (%.1f GB per step) exceed the 126 MB L2" % (h2d / 1e9),
+                   "parallelism": "pairs sharded over %d GPU(s), one all-gather of results per step" % world},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "moments_kernel (fused gather + UME moments)", "bound": "hbm",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": mom_avg_ms,
+                     "launches_timed": mom_n, "peak_source": peaks_note + " (MEASURED_PEAKS.json hbm_gbs)"},
+        "stages": stages,
+    }
+    if not args.no_cpu_baseline and world >= 1:
+        threads = os.cpu_count() or 1
+        from oracle import pytorch3d_ops as p3d
+        n_cpu = max(1, min(args.cpu_baseline_pairs, pairs))
+        cpu_reference_pairs(batch_np, [0], threads)                     # warm-up pair
+        sec = cpu_reference_pairs(batch_np, list(range(n_cpu)), threads)
+        line["cpu_baseline"] = {"value": n_cpu / sec, "unit": UNIT, "cores": p3d.c_num_threads(), "kind": "port",
+                                "sample": "%d pairs of the same batch, %.1f s (oracle port: numpy + OpenMP C ball_query)"
+                                          % (n_cpu, sec)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

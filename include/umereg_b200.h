@@ -128,6 +128,23 @@ int ume_knn1_gather_f32(const float* q, const float* p, const float* x, int B, i
                         unsigned flags, int64_t* idx, float* d2, float* out, void* ws, size_t ws_bytes,
                         void* stream);
 
+/* ---------------------------------------------------------------- stage profiler
+ * When enabled, every stage brackets its kernel launches with CUDA events on the launching
+ * stream; ume_profile_read() synchronises those events and returns the accumulated device time
+ * and the number of brackets of one stage since the last reset.  Used by bench.py for the
+ * per-kernel durations behind the roofline figures; off by default. */
+#define UME_PROF_GRID      0   /* search-grid build (bbox, count, scan, scatter)   */
+#define UME_PROF_MOMENTS   1   /* fused gather + moment kernel                     */
+#define UME_PROF_ORTHO     2   /* descriptor orthonormalisation                    */
+#define UME_PROF_CDIST     3   /* distance GEMM + arg-min                          */
+#define UME_PROF_RIGID     4   /* rigid solve                                      */
+#define UME_PROF_BALLQUERY 5
+#define UME_PROF_KNN       6
+#define UME_PROF_SLOTS     8
+void ume_profile_enable(int on);
+void ume_profile_reset(void);
+int ume_profile_read(int slot, double* total_ms, uint64_t* launches);
+
 /* ---------------------------------------------------------------- counters
  * Number of kernels this library has launched since load (all threads); bench.py reports the
  * difference over the timed region as `gpu_launches`. */

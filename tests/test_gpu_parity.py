@@ -157,7 +157,7 @@ def test_hot_path_against_reference_golden(ume, golden, name):
     # distances on the REFERENCE's matrices, so that each stage is pinned on its own
     D = host(ume.ume_cdist(dev(g["F_src"]), dev(g["F_tgt"])))
     D64 = orc.ume_cdist(g["F_src"], g["F_tgt"], dtype=np.float64)
-    assert np.abs(D - D64).max() < 5e-4                      # sqrt amplifies fp32 rounding near D = 0
+    assert np.abs(D - D64).max() < 3e-3                      # sqrt amplifies fp32 rounding near D = 0 (the reference: 1.5e-3)
     assert np.abs(D - D64)[D64 > 0.05].max() < 2e-5
     assert np.abs(D - g["D"]).max() < 2e-3                   # the reference's own mm-form cdist noise (SURVEY §4 i)
     # arg-min: equal to the reference's wherever the best-vs-second gap is above fp32 noise
@@ -182,7 +182,8 @@ def test_hot_path_against_reference_golden(ume, golden, name):
     # distance to that oracle where that is larger (ill-conditioned hypotheses)
     assert (ang <= np.maximum(1e-4, 2 * ang_ref)).all(), (ang.max(), ang_ref.max())
     assert (terr <= np.maximum(1e-4, 2 * terr_ref)).all(), (terr.max(), terr_ref.max())
-    assert np.abs(host(Dp) - Dp64).max() < 5e-4
+    assert np.abs(host(Dp) - Dp64).max() < 3e-3             # sqrt near 0, as for D above
+    assert np.abs(host(Dp) - Dp64)[Dp64 > 0.05].max(initial=0) < 5e-5
     assert np.array_equal(host(T)[:, 3], np.tile(np.array([0, 0, 0, 1], np.float32), (len(G), 1)))
 
 
@@ -253,7 +254,7 @@ def test_cdist_against_fp64_oracle(ume, C, n1, n2):
         assert np.abs(D64 - orc.ume_cdist(F1, F2, dtype=np.float64)).max() < 1e-6
     D = host(ume.ume_cdist(dev(F1), dev(F2)))
     assert D.shape == (2, n1, n2)
-    assert np.abs(D - D64)[D64 > 0.05].max() < 5e-5
+    assert np.abs(D - D64)[D64 > 0.05].max(initial=0) < 5e-5   # (C = 4: every subspace is the whole space, D = 0)
     assert np.abs(D - D64).max() < 3e-3
     assert D.min() >= 0 and D.max() <= 2.0 + 1e-6
     Qt, rank = ume.ume_descriptors(dev(F1), return_rank=True)

@@ -77,6 +77,9 @@ def _bind(lib):
         "ume_last_error": (c.c_char_p, []),
         "ume_status_string": (c.c_char_p, [i32]),
         "ume_launch_count": (c.c_uint64, []),
+        "ume_profile_enable": (None, [i32]),
+        "ume_profile_reset": (None, []),
+        "ume_profile_read": (i32, [i32, c.POINTER(c.c_double), c.POINTER(c.c_uint64)]),
         "ume_ball_query_workspace_bytes": (sz, [i32, i32, i32, i32]),
         "ume_ball_query_f32": (i32, [vp, vp, i32, i32, i32, i32, f32, u32, vp, vp, vp, vp, vp, sz, vp]),
         "ume_moments_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
@@ -97,6 +100,7 @@ def _bind(lib):
 
 
 EXPORTED_SYMBOLS = ["ume_abi_version", "ume_last_error", "ume_status_string", "ume_launch_count",
+                    "ume_profile_enable", "ume_profile_reset", "ume_profile_read",
                     "ume_ball_query_workspace_bytes", "ume_ball_query_f32", "ume_moments_workspace_bytes",
                     "ume_moments_f32", "ume_orthonormalize_f32", "ume_cdist_workspace_bytes", "ume_cdist_f32",
                     "ume_pair_dist_f32", "ume_rigid_solve_f32", "ume_knn1_workspace_bytes",
@@ -133,3 +137,24 @@ def check(status, what=""):
 
 def launch_count():
     return int(lib().ume_launch_count())
+
+
+PROF_SLOTS = {"grid": 0, "moments": 1, "ortho": 2, "cdist": 3, "rigid": 4, "ball_query": 5, "knn": 6}
+
+
+def profile_enable(on=True):
+    lib().ume_profile_enable(1 if on else 0)
+
+
+def profile_reset():
+    lib().ume_profile_reset()
+
+
+def profile_read():
+    """{stage: (total_ms, brackets)} accumulated since the last reset (synchronises the events)."""
+    out = {}
+    for name, slot in PROF_SLOTS.items():
+        ms, n = ctypes.c_double(0.0), ctypes.c_uint64(0)
+        check(lib().ume_profile_read(slot, ctypes.byref(ms), ctypes.byref(n)), "profile_read")
+        out[name] = (ms.value, int(n.value))
+    return out

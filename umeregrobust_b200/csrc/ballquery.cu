@@ -116,6 +116,7 @@ extern "C" int ume_ball_query_f32(const float* p1, const float* p2, int B, int P
     auto kern = fma ? ball_query_kernel<true> : ball_query_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     UME_REQUIRE(e == cudaSuccess, UME_ERR_CUDA, "ball_query: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    ProfScope prof(UME_PROF_BALLQUERY, stream);
     kern<<<(unsigned)((size_t)B * P1), kNT, smem, stream>>>(p);
     count_launch();
     return check_launch("ball_query_kernel");

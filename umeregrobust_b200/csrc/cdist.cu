@@ -144,6 +144,7 @@ extern "C" int ume_cdist_f32(const float* Qt1, const float* Qt2, int B, int n1, 
     cudaError_t e = cudaFuncSetAttribute(cdist_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     UME_REQUIRE(e == cudaSuccess, UME_ERR_CUDA, "cdist: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     dim3 grid((unsigned)((n1 + kTile - 1) / kTile), (unsigned)B);
+    ProfScope prof(UME_PROF_CDIST, stream);
     cdist_simt_kernel<<<grid, 256, smem, stream>>>(Qt1, Qt2, n1, n2, C, D, argmin, dmin);
     count_launch();
     return check_launch("cdist_simt_kernel");

@@ -2,6 +2,8 @@
 #include "ume_common.cuh"
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <stdarg.h>
 
 namespace ume {
@@ -28,9 +30,72 @@ int check_launch(const char* what) {
 }
 
 const char* last_error() { return g_err; }
+
+// ---------------------------------------------------------------- stage profiler
+// Optional CUDA-event bracket around each stage's kernel launches, on the launching stream.
+// Off by default; bench.py switches it on for the timed region to get the per-kernel durations
+// the roofline figures are computed from.
+namespace {
+struct ProfSlot {
+    std::vector<cudaEvent_t> ev;     // pairs (start, stop)
+    size_t used = 0;                 // events handed out and not yet folded into total
+    double total_ms = 0.0;
+    uint64_t n = 0;
+};
+std::mutex g_prof_mu;
+std::atomic<int> g_prof_on{0};
+ProfSlot g_prof[UME_PROF_SLOTS];
+
+void prof_fold(ProfSlot& s) {        // caller holds the mutex
+    for (size_t i = 0; i + 1 < s.used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(s.ev[i + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, s.ev[i], s.ev[i + 1]) == cudaSuccess) {
+            s.total_ms += ms;
+            s.n += 1;
+        }
+    }
+    s.used = 0;
+}
+}  // namespace
+
+int prof_begin(int slot, cudaStream_t stream) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return -1;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfSlot& s = g_prof[slot];
+    if (s.used + 2 > 8192) prof_fold(s);
+    while (s.ev.size() < s.used + 2) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return -1;
+        s.ev.push_back(e);
+    }
+    const int at = (int)s.used;
+    s.used += 2;
+    cudaEventRecord(s.ev[at], stream);
+    return at;
+}
+
+void prof_end(int slot, int token, cudaStream_t stream) {
+    if (token < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof[slot].ev[token + 1], stream);
+}
 uint64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 
 }  // namespace ume
+
+extern "C" void ume_profile_enable(int on) { ume::g_prof_on.store(on ? 1 : 0); }
+extern "C" void ume_profile_reset(void) {
+    std::lock_guard<std::mutex> lk(ume::g_prof_mu);
+    for (auto& s : ume::g_prof) { ume::prof_fold(s); s.total_ms = 0.0; s.n = 0; }
+}
+extern "C" int ume_profile_read(int slot, double* total_ms, uint64_t* launches) {
+    if (slot < 0 || slot >= UME_PROF_SLOTS) return UME_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(ume::g_prof_mu);
+    ume::prof_fold(ume::g_prof[slot]);
+    if (total_ms) *total_ms = ume::g_prof[slot].total_ms;
+    if (launches) *launches = ume::g_prof[slot].n;
+    return UME_OK;
+}
 
 extern "C" int ume_abi_version(void) { return UME_ABI_VERSION; }
 extern "C" const char* ume_last_error(void) { return ume::last_error(); }

@@ -210,6 +210,7 @@ int grid_build(const float* pts, const float* q, int B, int N, int nq, float exp
     UME_REQUIRE(ws.ok(), UME_ERR_WORKSPACE, "grid_build: workspace too small (%zu needed, %zu given)",
                 ws.used, ws.size);
 
+    ProfScope prof(UME_PROF_GRID, stream);
     grid_init_kernel<<<(B * 6 + 127) / 128, 128, 0, stream>>>(bbox, B);
     if (nq > 0) {
         dim3 g((unsigned)min((nq + 255) / 256, 64), (unsigned)B);

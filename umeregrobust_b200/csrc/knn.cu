@@ -120,6 +120,7 @@ extern "C" int ume_knn1_gather_f32(const float* q, const float* pcl, const float
     if (rc != UME_OK) return rc;
     p.q = q; p.x = x; p.idx = idx; p.d2 = d2; p.out = out; p.P1 = P1; p.U = U;
     dim3 grid((unsigned)((P1 + 7) / 8), (unsigned)B);
+    ProfScope prof(UME_PROF_KNN, stream);
     if (flags & UME_FLAG_FMA_DIST) knn1_kernel<true><<<grid, 256, 0, stream>>>(p);
     else knn1_kernel<false><<<grid, 256, 0, stream>>>(p);
     count_launch();

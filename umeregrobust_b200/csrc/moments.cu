@@ -196,6 +196,7 @@ int launch_moments(const MomentsParams& p, int B, bool fma, cudaStream_t stream)
     auto kern = fma ? moments_kernel<Acc, true> : moments_kernel<Acc, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     UME_REQUIRE(e == cudaSuccess, UME_ERR_CUDA, "moments: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    ProfScope prof(UME_PROF_MOMENTS, stream);
     kern<<<(unsigned)((size_t)B * p.n), kNT, smem, stream>>>(p);
     count_launch();
     return check_launch("moments_kernel");

@@ -182,6 +182,7 @@ extern "C" int ume_orthonormalize_f32(const float* F, int64_t nmat, int C, float
     const int64_t blocks = (nmat + wpb - 1) / wpb;
     UME_REQUIRE(blocks < 0x7fffffffll, UME_ERR_UNSUPPORTED, "ume_orthonormalize_f32: too many matrices");
     const int rpl = (C + 31) / 32;
+    ProfScope prof(UME_PROF_ORTHO, stream);
     if (rpl == 1) ortho_kernel<1><<<(unsigned)blocks, wpb * 32, 0, stream>>>(F, nmat, C, Qt, rank);
     else if (rpl == 2) ortho_kernel<2><<<(unsigned)blocks, wpb * 32, 0, stream>>>(F, nmat, C, Qt, rank);
     else if (rpl <= 4) ortho_kernel<4><<<(unsigned)blocks, wpb * 32, 0, stream>>>(F, nmat, C, Qt, rank);

@@ -187,6 +187,7 @@ extern "C" int ume_rigid_solve_f32(const float* G, const float* H, const int64_t
     const int64_t total = (int64_t)B * nm;
     const int64_t blocks = (total + 31) / 32;
     UME_REQUIRE(blocks < 0x7fffffffll, UME_ERR_UNSUPPORTED, "ume_rigid_solve_f32: too many hypotheses");
+    ProfScope prof(UME_PROF_RIGID, stream);
     rigid_kernel<<<(unsigned)blocks, 256, 0, stream>>>(G, H, gi, hi, offG, offH, total, nG, nH, nm, C, T);
     count_launch();
     return check_launch("rigid_kernel");

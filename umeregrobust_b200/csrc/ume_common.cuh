@@ -17,6 +17,16 @@ void count_launch(int n = 1);
 int check_launch(const char* what);   // cudaGetLastError -> UME_OK / UME_ERR_CUDA
 const char* last_error();
 uint64_t launches();
+int prof_begin(int slot, cudaStream_t stream);            // -1 when profiling is off
+void prof_end(int slot, int token, cudaStream_t stream);
+
+// RAII bracket: events around everything launched on `stream` during its lifetime
+struct ProfScope {
+    int slot, token;
+    cudaStream_t stream;
+    ProfScope(int s, cudaStream_t st) : slot(s), token(prof_begin(s, st)), stream(st) {}
+    ~ProfScope() { prof_end(slot, token, stream); }
+};
 
 #define UME_REQUIRE(cond, status, ...)            \
     do {                                          \
