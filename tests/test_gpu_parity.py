@@ -19,7 +19,7 @@ def ume():
     from umeregrobust_b200 import _lib
     _lib.lib()                                   # fails loudly when the CUDA library is missing
     yield u
-    u.config.update(fma_dist=False, cell_div2=False, cdist_impl=0)
+    u.config.update(fma_dist=False, cell_div2=False, cdist_impl=None)
 
 
 def dev(x):
@@ -376,3 +376,32 @@ def test_register_hypotheses_matches_oracle_noisy_pair(ume):
     ang32 = orc.rotation_angle_rad(ref32["T"][same32][:, :3, :3], ref["T"][same32][:, :3, :3])
     assert np.median(ang) < 1e-4 and np.median(terr) < 1e-4, (np.median(ang), np.median(terr))
     assert np.percentile(ang, 90) <= max(1e-4, 2 * np.percentile(ang32, 90))
+
+
+# ----------------------------------------------------------------------------- tcgen05 distance GEMM (impl 1)
+@pytest.mark.parametrize("C,B,n1,n2", [(32, 2, 64, 32), (32, 1, 100, 70), (32, 3, 300, 257), (64, 2, 96, 130),
+                                       (32, 1, 1024, 1024), (64, 1, 33, 31)])
+def test_cdist_tcgen05_matches_fp64_and_simt(ume, C, B, n1, n2):
+    rng = np.random.default_rng(C + n1)
+    F1 = rng.normal(size=(B, n1, C, 4)).astype(np.float32)
+    F2 = rng.normal(size=(B, n2, C, 4)).astype(np.float32)
+    k = min(5, n1, n2)
+    F2[:, :k] = F1[:, :k] @ (rng.normal(size=(4, 4)) + 3 * np.eye(4)).astype(np.float32)     # D ~ 0 entries
+    Q1, Q2 = ume.ume_descriptors(dev(F1)), ume.ume_descriptors(dev(F2))
+    D0, am0, dm0 = ume.descriptor_cdist(Q1, Q2, want_D=True, want_argmin=True, impl=0)
+    D1, am1, dm1 = ume.descriptor_cdist(Q1, Q2, want_D=True, want_argmin=True, impl=1)
+    torch.cuda.synchronize()
+    D64 = orc.ume_cdist_gram(F1, F2)
+    D0, D1 = host(D0), host(D1)
+    assert np.isfinite(D1).all()
+    assert np.abs(D1 - D64)[D64 > 0.05].max(initial=0) < 5e-5        # 3xTF32 split: fp32-grade
+    assert np.abs(D1 - D64).max() < 3e-3
+    assert np.abs(D1 - D0)[D64 > 0.05].max(initial=0) < 5e-5
+    assert np.array_equal(host(am1), np.argmin(D1, -1))               # fused arg-min == arg-min of the written D
+    assert np.abs(host(dm1) - D1.min(-1)).max() == 0
+    srt = np.sort(D64, -1)
+    clear = (srt[..., 1] - srt[..., 0]) > 1e-4 if n2 > 1 else np.ones((B, n1), bool)
+    assert np.array_equal(host(am1)[clear], np.argmin(D64, -1)[clear])
+    # arg-min only (no D written)
+    _, am2, dm2 = ume.descriptor_cdist(Q1, Q2, want_D=False, want_argmin=True, impl=1)
+    assert np.array_equal(host(am2), host(am1)) and np.array_equal(host(dm2), host(dm1))

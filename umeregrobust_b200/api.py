@@ -20,7 +20,8 @@ _KNN = collections.namedtuple("_KNN", ["dists", "idx", "knn"])
 #              pytorch3d's CUDA kernel) instead of separately rounded mul/add (pytorch3d CPU build)
 #   cell_div2: search grid with cell = radius / 2
 #   cdist_impl: 0 = fp32 SIMT distance kernel, 1 = tcgen05 tensor-core kernel
-config = {"fma_dist": False, "cell_div2": False, "cdist_impl": 0}
+#               (C = 32 / 64 only), None = tensor cores whenever the channel count allows
+config = {"fma_dist": False, "cell_div2": False, "cdist_impl": None}
 
 _workspaces = {}
 
@@ -216,6 +217,8 @@ def descriptor_cdist(Qt1, Qt2, want_D=True, want_argmin=False, impl=None):
     if Qt2.shape[0] != B or Qt2.shape[3] != C or Qt1.shape[2] != 4 or Qt2.shape[2] != 4:
         raise ValueError("descriptor_cdist: shapes %s and %s do not agree" % (tuple(Qt1.shape), tuple(Qt2.shape)))
     impl = config["cdist_impl"] if impl is None else impl
+    if impl is None:
+        impl = 1 if C in (32, 64) else 0
     dev = Qt1.device
     D = torch.empty((B, n1, n2), dtype=torch.float32, device=dev) if want_D else None
     am = torch.empty((B, n1), dtype=torch.int64, device=dev) if want_argmin else None
