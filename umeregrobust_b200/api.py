@@ -49,6 +49,18 @@ def _workspace(nbytes, device):
     return ws
 
 
+def _out(buf, key, shape, dtype, device):
+    """Output tensor: fresh, or — when the caller passes an arena dict `buf` — the arena's tensor
+    of that name, reused across calls (no allocator traffic in steady state, stable pointers)."""
+    if buf is None:
+        return torch.empty(shape, dtype=dtype, device=device)
+    t = buf.get(key)
+    if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != device:
+        t = torch.empty(shape, dtype=dtype, device=device)
+        buf[key] = t
+    return t
+
+
 def _dev_f32(t, name, ndim=None):
     if not isinstance(t, torch.Tensor):
         raise TypeError("%s must be a torch.Tensor" % name)
@@ -145,7 +157,7 @@ def knn1_transfer(q, p, x):
 
 
 # ----------------------------------------------------------------------------- UME moments
-def ume_moments(pts, kpts, feat, K, radius, return_centered=False, return_count=False):
+def ume_moments(pts, kpts, feat, K, radius, return_centered=False, return_count=False, buf=None, tag=""):
     """Fused ball-query + gather + moment build.  F (B,n,C,4) exactly as evaluate.py:50-60
     produces it; optionally the keypoint-centred matrix Fc (same column space) and the
     neighbour count per keypoint."""
@@ -158,9 +170,9 @@ def ume_moments(pts, kpts, feat, K, radius, return_centered=False, return_count=
                          (tuple(pts.shape), tuple(kpts.shape), tuple(feat.shape)))
     n, C = kpts.shape[1], feat.shape[2]
     dev = pts.device
-    F = torch.empty((B, n, C, 4), dtype=torch.float32, device=dev)
-    Fc = torch.empty_like(F) if return_centered else None
-    cnt = torch.empty((B, n), dtype=torch.int32, device=dev) if return_count else None
+    F = _out(buf, "F" + tag, (B, n, C, 4), torch.float32, dev)
+    Fc = _out(buf, "Fc" + tag, (B, n, C, 4), torch.float32, dev) if return_centered else None
+    cnt = _out(buf, "cnt" + tag, (B, n), torch.int32, dev) if return_count else None
     with torch.cuda.device(dev):
         L = _lib.lib()
         ws = _workspace(L.ume_moments_workspace_bytes(B, N, n, C, int(K)), dev)
@@ -191,7 +203,7 @@ def create_local_ume_matrix(nn_pts, nn_feat):
 
 
 # ----------------------------------------------------------------------------- descriptors / distances
-def ume_descriptors(ume, return_rank=False):
+def ume_descriptors(ume, return_rank=False, buf=None, tag=""):
     """Orthonormal basis rows Qt (..., 4, C) of the column space of each (..., C, 4) UME matrix
     (the QR of utils/loc_utils.py:9,11 up to the choice of basis)."""
     ume = _dev_f32(ume, "ume")
@@ -199,15 +211,15 @@ def ume_descriptors(ume, return_rank=False):
         raise ValueError("ume_descriptors: expected (..., C, 4), got %s" % (tuple(ume.shape),))
     C = ume.shape[-2]
     nmat = ume.numel() // (C * 4) if C > 0 else 0
-    Qt = torch.empty(ume.shape[:-2] + (4, C), dtype=torch.float32, device=ume.device)
-    rank = torch.empty(ume.shape[:-2], dtype=torch.int32, device=ume.device) if return_rank else None
+    Qt = _out(buf, "Qt" + tag, tuple(ume.shape[:-2]) + (4, C), torch.float32, ume.device)
+    rank = _out(buf, "rank" + tag, tuple(ume.shape[:-2]), torch.int32, ume.device) if return_rank else None
     with torch.cuda.device(ume.device):
         rc = _lib.lib().ume_orthonormalize_f32(_ptr(ume), nmat, C, _ptr(Qt), _ptr(rank), _stream())
     _lib.check(rc, "ume_descriptors")
     return (Qt, rank) if return_rank else Qt
 
 
-def descriptor_cdist(Qt1, Qt2, want_D=True, want_argmin=False, impl=None):
+def descriptor_cdist(Qt1, Qt2, want_D=True, want_argmin=False, impl=None, buf=None):
     """All-pairs D = sqrt(4 - |Q1^T Q2|_F^2) between descriptor sets (B,n1,4,C) x (B,n2,4,C), with
     the row arg-min (first index on ties) fused.  Returns (D or None, argmin or None, dmin or None)."""
     Qt1 = _dev_f32(Qt1, "Qt1", 4)
@@ -220,9 +232,9 @@ def descriptor_cdist(Qt1, Qt2, want_D=True, want_argmin=False, impl=None):
     if impl is None:
         impl = 1 if C in (32, 64) else 0
     dev = Qt1.device
-    D = torch.empty((B, n1, n2), dtype=torch.float32, device=dev) if want_D else None
-    am = torch.empty((B, n1), dtype=torch.int64, device=dev) if want_argmin else None
-    dm = torch.empty((B, n1), dtype=torch.float32, device=dev) if want_argmin else None
+    D = _out(buf, "D", (B, n1, n2), torch.float32, dev) if want_D else None
+    am = _out(buf, "argmin", (B, n1), torch.int64, dev) if want_argmin else None
+    dm = _out(buf, "dmin", (B, n1), torch.float32, dev) if want_argmin else None
     with torch.cuda.device(dev):
         L = _lib.lib()
         nbytes = L.ume_cdist_workspace_bytes(B, n1, n2, C, impl)
@@ -243,7 +255,7 @@ def ume_cdist(ume1, ume2):
 
 
 # ----------------------------------------------------------------------------- rigid solve
-def rigid_solve(G, H, gi=None, hi=None, offG=None, offH=None):
+def rigid_solve(G, H, gi=None, hi=None, offG=None, offH=None, buf=None):
     """Batched closed-form rigid hypotheses.  G (B,nG,C,4), H (B,nH,C,4); hypothesis (b,i) pairs
     G[b,gi[b,i]] with H[b,hi[b,i]] (identity when the index is None).  offG/offH: the points the
     moments are relative to (for the centred `Fc` matrices).  Returns T (B,nm,4,4)."""
@@ -261,7 +273,7 @@ def rigid_solve(G, H, gi=None, hi=None, offG=None, offH=None):
     if offG is not None:
         offG = _dev_f32(offG, "offG", 3)
         offH = _dev_f32(offH, "offH", 3)
-    T = torch.empty((B, nm, 4, 4), dtype=torch.float32, device=G.device)
+    T = _out(buf, "T", (B, nm, 4, 4), torch.float32, G.device)
     with torch.cuda.device(G.device):
         rc = _lib.lib().ume_rigid_solve_f32(_ptr(G), _ptr(H), _ptr(gi), _ptr(hi), _ptr(offG), _ptr(offH), B, nG, nH,
                                             nm, C, _ptr(T), _stream())
@@ -365,7 +377,7 @@ class ume_kp_layer(torch.nn.Module):
 
 # ----------------------------------------------------------------------------- fused hot path
 def register_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K, radius, want_D=False,
-                        centered=True):
+                        centered=True, buf=None):
     """evaluate.py:206-257 for a whole batch, without the host-RNG sub-sampling (:233-245): UME
     matrices for both clouds, subspace distances with fused arg-min, one rigid hypothesis per
     source keypoint from its best-matching target keypoint.
@@ -373,20 +385,31 @@ def register_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K,
     centered=True runs descriptors and the solve on the keypoint-centred moments (same column
     space / same transform, smaller numbers, closer to the exact answer than the reference's own
     fp32); centered=False follows the reference's absolute-coordinate arithmetic.
+    `buf`: an arena dict; when given, every output lives in it and is REUSED by the next call with
+    the same shapes (the returned tensors are then only valid until that next call).
     Returns dict(F_src, F_tgt, match (B,n,2) int64, dmin (B,n), T (B,n,4,4), D or None)."""
     if centered:
-        F_src, Fc_src = ume_moments(src_pts, src_kp, src_feat, K, radius, return_centered=True)
-        F_tgt, Fc_tgt = ume_moments(tgt_pts, tgt_kp, tgt_feat, K, radius, return_centered=True)
+        F_src, Fc_src = ume_moments(src_pts, src_kp, src_feat, K, radius, return_centered=True, buf=buf, tag="_src")
+        F_tgt, Fc_tgt = ume_moments(tgt_pts, tgt_kp, tgt_feat, K, radius, return_centered=True, buf=buf, tag="_tgt")
         A, Bm = Fc_src, Fc_tgt
     else:
-        F_src = ume_moments(src_pts, src_kp, src_feat, K, radius)
-        F_tgt = ume_moments(tgt_pts, tgt_kp, tgt_feat, K, radius)
+        F_src = ume_moments(src_pts, src_kp, src_feat, K, radius, buf=buf, tag="_src")
+        F_tgt = ume_moments(tgt_pts, tgt_kp, tgt_feat, K, radius, buf=buf, tag="_tgt")
         A, Bm = F_src, F_tgt
-    D, am, dm = descriptor_cdist(ume_descriptors(A), ume_descriptors(Bm), want_D=want_D, want_argmin=True)
+    D, am, dm = descriptor_cdist(ume_descriptors(A, buf=buf, tag="_src"), ume_descriptors(Bm, buf=buf, tag="_tgt"),
+                                 want_D=want_D, want_argmin=True, buf=buf)
     if centered:
-        T = rigid_solve(A, Bm, None, am, src_kp, tgt_kp)
+        T = rigid_solve(A, Bm, None, am, src_kp, tgt_kp, buf=buf)
     else:
-        T = rigid_solve(A, Bm, None, am)
+        T = rigid_solve(A, Bm, None, am, buf=buf)
     B, n = am.shape
-    match = torch.stack([torch.arange(n, device=am.device).expand(B, n), am], dim=-1)
+    if buf is not None and "arange" in buf and tuple(buf["arange"].shape) == (B, n) and buf["arange"].device == am.device:
+        ar = buf["arange"]
+    else:
+        ar = torch.arange(n, device=am.device).expand(B, n)
+        if buf is not None:
+            buf["arange"] = ar
+    match = _out(buf, "match", (B, n, 2), torch.int64, am.device)
+    match[..., 0] = ar
+    match[..., 1] = am
     return dict(F_src=F_src, F_tgt=F_tgt, match=match, dmin=dm, T=T, D=D)

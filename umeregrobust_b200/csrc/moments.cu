@@ -135,7 +135,7 @@ struct GenAcc {
 };
 
 template <typename Acc, bool kFma>
-__global__ void __launch_bounds__(kNT) moments_kernel(MomentsParams p) {
+__global__ void __launch_bounds__(kNT, 4) moments_kernel(MomentsParams p) {
     extern __shared__ float4 list[];            // cap entries; reused as reduction scratch
     __shared__ CollectSmem sm;
     __shared__ float s_f0[256];

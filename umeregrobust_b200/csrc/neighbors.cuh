@@ -12,8 +12,8 @@
 namespace ume {
 
 static constexpr int kMaxRows = 64;       // (2*div+2)^2 <= 36 cell rows per query
-static constexpr int kHistBins = 2048;
-static constexpr int kBitmapWords = 128;  // bin width <= 4096 indices  ->  N <= 2048*4096
+static constexpr int kHistBins = 512;
+static constexpr int kBitmapWords = 512;  // bin width <= 16384 indices  ->  N <= 512*16384
 
 struct CollectSmem {
     int seg_start[kMaxRows];
@@ -30,61 +30,67 @@ struct CollectSmem {
 template <int NT>
 UME_DEVI void collect_rows(CollectSmem& sm, const GridHeader& h, const int* __restrict__ cs, float kx,
                            float ky, float kz, float radius) {
-    const float r = fabsf(radius);
-    const float mx = r * 1e-4f + fabsf(kx) * 1e-6f + 1e-7f;
-    const float my = r * 1e-4f + fabsf(ky) * 1e-6f + 1e-7f;
-    const float mz = r * 1e-4f + fabsf(kz) * 1e-6f + 1e-7f;
-    const int cx0 = cell_coord(kx - r - mx, h.ox, h.inv_s, h.nx);
-    const int cx1 = cell_coord(kx + r + mx, h.ox, h.inv_s, h.nx);
-    const int cy0 = cell_coord(ky - r - my, h.oy, h.inv_s, h.ny);
-    const int cy1 = cell_coord(ky + r + my, h.oy, h.inv_s, h.ny);
-    const int cz0 = cell_coord(kz - r - mz, h.oz, h.inv_s, h.nz);
-    const int cz1 = cell_coord(kz + r + mz, h.oz, h.inv_s, h.nz);
-    const int nyr = cy1 - cy0 + 1, nzr = cz1 - cz0 + 1;
-    int nrows = nyr * nzr;
-    if (nrows > kMaxRows) nrows = kMaxRows;     // cannot happen: cell >= radius/2 (see grid_params_kernel)
-    const float rr = (r + 4.f * (mx + my + mz));
-    const float rr2 = rr * rr;
-    for (int row = threadIdx.x; row < nrows; row += NT) {
-        const int iy = cy0 + row % nyr, iz = cz0 + row / nyr;
-        // prune rows / trim the x range by the distance from the query to the cell slab; the
-        // outermost cells also hold clamped coordinates, so they are treated as unbounded
-        float dy = 0.f, dz = 0.f;
-        {
-            float lo = h.oy + (float)iy * h.s, hi = lo + h.s;
-            if (iy > 0 && ky < lo) dy = lo - ky;
-            if (iy < h.ny - 1 && ky > hi) dy = ky - hi;
-            lo = h.oz + (float)iz * h.s; hi = lo + h.s;
-            if (iz > 0 && kz < lo) dz = lo - kz;
-            if (iz < h.nz - 1 && kz > hi) dz = kz - hi;
-        }
-        const float rem2 = rr2 - dy * dy - dz * dz;
+    static_assert(NT >= kMaxRows, "one thread per candidate row");
+    if (threadIdx.x < kMaxRows) {
+        const float r = fabsf(radius);
+        const float mx = r * 1e-4f + fabsf(kx) * 1e-6f + 1e-7f;
+        const float my = r * 1e-4f + fabsf(ky) * 1e-6f + 1e-7f;
+        const float mz = r * 1e-4f + fabsf(kz) * 1e-6f + 1e-7f;
+        const int cx0 = cell_coord(kx - r - mx, h.ox, h.inv_s, h.nx);
+        const int cx1 = cell_coord(kx + r + mx, h.ox, h.inv_s, h.nx);
+        const int cy0 = cell_coord(ky - r - my, h.oy, h.inv_s, h.ny);
+        const int cy1 = cell_coord(ky + r + my, h.oy, h.inv_s, h.ny);
+        const int cz0 = cell_coord(kz - r - mz, h.oz, h.inv_s, h.nz);
+        const int cz1 = cell_coord(kz + r + mz, h.oz, h.inv_s, h.nz);
+        const int nyr = cy1 - cy0 + 1, nzr = cz1 - cz0 + 1;
+        int nrows = nyr * nzr;
+        if (nrows > kMaxRows) nrows = kMaxRows;     // cannot happen: cell >= radius/2 (see grid_params_kernel)
+        const float rr = (r + 4.f * (mx + my + mz));
+        const float rr2 = rr * rr;
+        const int row = threadIdx.x;
         int s = 0, n = 0;
-        if (rem2 > 0.f) {
-            const float half = sqrtf(rem2) * 1.0001f + mx;
-            const int tx0 = max(cx0, cell_coord(kx - half, h.ox, h.inv_s, h.nx));
-            const int tx1 = min(cx1, cell_coord(kx + half, h.ox, h.inv_s, h.nx));
-            if (tx1 >= tx0) {
-                const int base = (iz * h.ny + iy) * h.nx;
-                s = cs[base + tx0];
-                n = cs[base + tx1 + 1] - s;
+        if (row < nrows) {
+            const int iy = cy0 + row % nyr, iz = cz0 + row / nyr;
+            // prune rows / trim the x range by the distance from the query to the cell slab; the
+            // outermost cells also hold clamped coordinates, so they are treated as unbounded
+            float dy = 0.f, dz = 0.f;
+            {
+                float lo = h.oy + (float)iy * h.s, hi = lo + h.s;
+                if (iy > 0 && ky < lo) dy = lo - ky;
+                if (iy < h.ny - 1 && ky > hi) dy = ky - hi;
+                lo = h.oz + (float)iz * h.s; hi = lo + h.s;
+                if (iz > 0 && kz < lo) dz = lo - kz;
+                if (iz < h.nz - 1 && kz > hi) dz = kz - hi;
             }
+            const float rem2 = rr2 - dy * dy - dz * dz;
+            if (rem2 > 0.f) {
+                const float half = sqrtf(rem2) * 1.0001f + mx;
+                const int tx0 = max(cx0, cell_coord(kx - half, h.ox, h.inv_s, h.nx));
+                const int tx1 = min(cx1, cell_coord(kx + half, h.ox, h.inv_s, h.nx));
+                if (tx1 >= tx0) {
+                    const int base = (iz * h.ny + iy) * h.nx;
+                    s = cs[base + tx0];
+                    n = cs[base + tx1 + 1] - s;
+                }
+            }
+            sm.seg_start[row] = s;
         }
-        sm.seg_start[row] = s;
-        sm.seg_prefix[row + 1] = n;       // lengths for now; prefix-summed below
+        // exclusive prefix of the run lengths over the (<= 64) rows: two warps, shuffle scan
+        const int lane = threadIdx.x & 31;
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(UME_FULL_MASK, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (threadIdx.x == 31) sm.warp_cnt[0] = incl;
+        if (threadIdx.x == 0) { sm.nrows = nrows; sm.count = 0; sm.seg_prefix[0] = 0; }
+        sm.seg_prefix[row + 1] = incl;               // second warp fixed up below
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        sm.seg_prefix[0] = 0;
-        for (int r_ = 0; r_ < nrows; ++r_) {
-            run += sm.seg_prefix[r_ + 1];
-            sm.seg_prefix[r_ + 1] = run;
-        }
-        sm.nrows = nrows;
-        sm.total = run;
-        sm.count = 0;
-    }
+    if (threadIdx.x >= 32 && threadIdx.x < kMaxRows) sm.seg_prefix[threadIdx.x + 1] += sm.warp_cnt[0];
+    __syncthreads();
+    if (threadIdx.x == 0) sm.total = sm.seg_prefix[sm.nrows];
     __syncthreads();
 }
 
@@ -96,17 +102,26 @@ UME_DEVI void scan_candidates(const CollectSmem& sm, const float4* __restrict__ 
                               float kz, float r2, Visit visit) {
     const int total = sm.total;
     int seg = 0;
-    for (int base = 0; base < total; base += NT) {
-        const int j = base + threadIdx.x;
-        const bool valid = j < total;
-        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-            while (j >= sm.seg_prefix[seg + 1]) ++seg;
-            c = __ldg(&sorted_b[sm.seg_start[seg] + (j - sm.seg_prefix[seg])]);
+    int seg_end = sm.seg_prefix[1];                       // run bounds live in registers; smem is only
+    int seg_off = sm.seg_start[0];                        // touched when a thread crosses into the next run
+    for (int base = 0; base < total; base += 2 * NT) {
+        const int j0 = base + threadIdx.x, j1 = j0 + NT;
+        const bool v0 = j0 < total, v1 = j1 < total;
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+        if (v0) {
+            while (j0 >= seg_end) { ++seg; seg_end = sm.seg_prefix[seg + 1]; seg_off = sm.seg_start[seg] - sm.seg_prefix[seg]; }
+            c0 = __ldg(&sorted_b[j0 + seg_off]);
         }
-        const float ex = __fsub_rn(c.x, kx), ey = __fsub_rn(c.y, ky), ez = __fsub_rn(c.z, kz);
-        const float d2 = dist2_ordered<kFma>(ex, ey, ez);
-        visit(valid && (d2 < r2), ex, ey, ez, d2, __float_as_int(c.w));
+        if (v1) {
+            while (j1 >= seg_end) { ++seg; seg_end = sm.seg_prefix[seg + 1]; seg_off = sm.seg_start[seg] - sm.seg_prefix[seg]; }
+            c1 = __ldg(&sorted_b[j1 + seg_off]);
+        }
+        const float ex0 = __fsub_rn(c0.x, kx), ey0 = __fsub_rn(c0.y, ky), ez0 = __fsub_rn(c0.z, kz);
+        const float ex1 = __fsub_rn(c1.x, kx), ey1 = __fsub_rn(c1.y, ky), ez1 = __fsub_rn(c1.z, kz);
+        const float d0 = dist2_ordered<kFma>(ex0, ey0, ez0);
+        const float d1 = dist2_ordered<kFma>(ex1, ey1, ez1);
+        visit(v0 && (d0 < r2), ex0, ey0, ez0, d0, __float_as_int(c0.w));
+        if (base + NT < total) visit(v1 && (d1 < r2), ex1, ey1, ez1, d1, __float_as_int(c1.w));   // block-uniform
     }
 }
 
@@ -166,7 +181,8 @@ UME_DEVI int select_kth_index(CollectSmem& sm, int K, int shift, Each each) {
             }
         }
     }
-    for (int i = tid; i < kBitmapWords; i += NT) sm.bitmap[i] = 0;
+    const int nwords = max(1, (1 << shift) >> 5);
+    for (int i = tid; i < nwords; i += NT) sm.bitmap[i] = 0;
     __syncthreads();
     const int bin = sm.sel_bin;
     const int need = K - sm.sel_below;                 // >= 1 indices wanted from the crossing bin
@@ -181,8 +197,8 @@ UME_DEVI int select_kth_index(CollectSmem& sm, int K, int shift, Each each) {
     if (warp == 0) {
         int run = 0;
         bool done = false;
-        for (int t = 0; t < kBitmapWords / 32 && !done; ++t) {
-            const unsigned word = sm.bitmap[t * 32 + lane];
+        for (int t = 0; t * 32 < nwords && !done; ++t) {
+            const unsigned word = (t * 32 + lane < nwords) ? sm.bitmap[t * 32 + lane] : 0u;
             const int pc = __popc(word);
             int incl = pc;
 #pragma unroll

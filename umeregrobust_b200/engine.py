@@ -28,14 +28,18 @@ class RegistrationEngine:
         self._streams = None
         self._staging = {}
         self._host_out = {}
+        self._arena = {}                 # outputs of register(): reused every call
+        self._chunk_arena = [{}, {}]     # per-stream outputs of register_host()
 
     # ------------------------------------------------------------------ device-resident batch
     def register(self, batch):
         """batch: dict with src_pts (B,N,3), src_feat (B,N,C), src_kp (B,n,3) and tgt_* on the
-        device.  Returns dict(T (B,n,4,4), match (B,n,2) int64, dmin (B,n), F_src, F_tgt, D|None)."""
+        device.  Returns dict(T (B,n,4,4), match (B,n,2) int64, dmin (B,n), F_src, F_tgt, D|None).
+        The outputs live in the engine's arena: they are overwritten by the next call (clone what
+        must survive) — no allocation happens in steady state."""
         return api.register_hypotheses(batch["src_pts"], batch["src_feat"], batch["src_kp"], batch["tgt_pts"],
                                        batch["tgt_feat"], batch["tgt_kp"], self.K, self.radius, want_D=self.want_D,
-                                       centered=self.centered)
+                                       centered=self.centered, buf=self._arena)
 
     # ------------------------------------------------------------------ host-resident batch
     def _stage(self, slot, key, shape, dtype):
@@ -86,7 +90,8 @@ class RegistrationEngine:
                         dev[k] = buf
                     out = api.register_hypotheses(dev["src_pts"], dev["src_feat"], dev["src_kp"], dev["tgt_pts"],
                                                   dev["tgt_feat"], dev["tgt_kp"], self.K, self.radius, want_D=False,
-                                                  centered=self.centered)
+                                                  centered=self.centered,
+                                                  buf=self._chunk_arena[slot] if hi - lo == cp else None)
                     T[lo:hi].copy_(out["T"], non_blocking=True)
                     match[lo:hi].copy_(out["match"][..., 1], non_blocking=True)
                     dmin[lo:hi].copy_(out["dmin"], non_blocking=True)
