@@ -38,6 +38,27 @@ K_NN, RADIUS = 750, 5.0
 METRIC, UNIT = "pairs_per_sec_kitti_shape_1024kp", "pairs/s"
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the driver wants exactly ONE JSON
+    line there.  Everything else is sent to stderr; the JSON line goes to the saved descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -149,7 +170,7 @@ def run_reference(args, wl):
                              "sample": "1 pair of the workload per step (oracle port: numpy + OpenMP C ball_query)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- CUDA arm
@@ -312,13 +333,14 @@ def run_b200(args, wl):
         line["cpu_baseline"] = {"value": n_cpu / sec, "unit": UNIT, "cores": p3d.c_num_threads(), "kind": "port",
                                 "sample": "%d pairs of the same batch, %.1f s (oracle port: numpy + OpenMP C ball_query)"
                                           % (n_cpu, sec)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse()
+    protect_stdout()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
