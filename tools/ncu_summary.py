@@ -24,6 +24,17 @@ KEEP = [
 ]
 
 
+TENSOR = [
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__ops_path_tensor_src_tf32_dst_fp32.avg.pct_of_peak_sustained_elapsed",
+    "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "smsp__mem_tensor_reads_op_ldt.sum.pct_of_peak_sustained_elapsed",
+    "smsp__mem_tensor_reads_op_utcmma_matrix_c.sum.pct_of_peak_sustained_elapsed",
+    "smsp__mem_tensor_writes_op_utcmma.sum.pct_of_peak_sustained_elapsed",
+]
+
+
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -36,7 +47,7 @@ def main():
             name = vals[hdr.index("Kernel Name")][:100]
             for h, u, v in zip(hdr, units, vals):
                 if h in KEEP or (h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")) \
-                        or "tensor" in h and "pct" in h:
+                        or h in TENSOR:
                     w.writerow([name, h, u, v])
     print("wrote", out)
 

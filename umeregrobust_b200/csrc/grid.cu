@@ -255,7 +255,7 @@ int grid_build(const float* pts, const float* q, int B, int N, int nq, float exp
     grid_params_kernel<<<(B + 127) / 128, 128, 0, stream>>>(bbox, hdr, B, expand, cell, cells_cap);
     cudaMemsetAsync(g_count, 0, (size_t)B * cells_cap * sizeof(int), stream);
     // CTAs per cloud: about two waves of the 148 SMs in total, at least ~2048 points per CTA
-    int G = (2 * 148 + B - 1) / B;
+    int G = (4 * 148) / B;
     G = max(1, min(G, min(64, N / 2048)));
     grid_rank_kernel<<<dim3((unsigned)G, (unsigned)B), kRankThreads, smem, stream>>>(pts, N, hdr, g_count, cells_cap, cell_of,
                                                                                    rank_of);

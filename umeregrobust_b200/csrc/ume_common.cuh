@@ -121,7 +121,9 @@ size_t grid_workspace_bytes(int B, int N, int cells_cap);
 int grid_build(const float* pts, const float* q, int B, int N, int nq, float expand, float cell,
                int cells_cap, Workspace& ws, GridView* view, cudaStream_t stream);
 
-static constexpr int kCellsCap = 32768;
+// Cells per cloud.  8192 keeps the binning kernel's shared-memory histogram at 32 KB (4 CTAs per SM)
+// and the cell table L1/L2-friendly; a KITTI-shape cloud at cell = radius needs ~4.6 k cells.
+static constexpr int kCellsCap = 8192;
 static constexpr int kMaxPoints = 8388608;
 
 }  // namespace ume
