@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(kNT) ball_query_kernel(BallQueryParams p) {
     const float kx = p.p1[(size_t)q * 3 + 0], ky = p.p1[(size_t)q * 3 + 1], kz = p.p1[(size_t)q * 3 + 2];
     const int K = p.K;
 
-    const int used = collect_neighbors<kFma, kNT>(
-        sm, list, p.cap, h, cs, sorted_b, N, kx, ky, kz, p.radius, K, [&](int len) {
+    const int used = collect_neighbors<kFma, kNT, true>(
+        sm, list, p.cap, h, cs, sorted_b, N, kx, ky, kz, p.radius, K, [&](int len, int) {
             // K <= cap, so this runs exactly once with the complete neighbourhood
             int P = 1;
             while (P < len) P <<= 1;

@@ -14,6 +14,9 @@ namespace ume {
 namespace {
 
 constexpr int kNT = 256;
+#ifndef UME_MOMENTS_MINB
+#define UME_MOMENTS_MINB 4
+#endif
 constexpr int kNW = kNT / 32;
 
 struct MomentsParams {
@@ -51,24 +54,31 @@ struct VecAcc {
             a[i][3] = fmaf(fv[i], nb.z, a[i][3]);
         }
     }
-    UME_DEVI void gather(const float4* list, int len, const float* __restrict__ feat_b) {
+    // entries whose row index exceeds T are not neighbours: their load is predicated off and they
+    // contribute zeros
+    UME_DEVI void gather(const float4* list, int len, int T, const float* __restrict__ feat_b) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int sub = lane / LPR, l = lane % LPR;
         constexpr int stride = kNW * RPW;
         const float* fl = feat_b + 4 * l;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
         int e = warp * RPW + sub;
         for (; e + 3 * stride < len; e += 4 * stride) {
             float4 nb[4], f[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) nb[u] = list[e + u * stride];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) f[u] = ldg_f4(fl + (size_t)__float_as_int(nb[u].w) * C);
+            for (int u = 0; u < 4; ++u) {
+                const int j = __float_as_int(nb[u].w);
+                f[u] = (j <= T) ? ldg_f4(fl + (size_t)j * C) : zero;
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) add(nb[u], f[u]);
         }
         for (; e < len; e += stride) {
             const float4 nb = list[e];
-            add(nb, ldg_f4(fl + (size_t)__float_as_int(nb.w) * C));
+            const int j = __float_as_int(nb.w);
+            add(nb, (j <= T) ? ldg_f4(fl + (size_t)j * C) : zero);
         }
     }
     // combine the RPW row groups of the warp, then lanes [0,LPR) hold the warp's C x 4 partial
@@ -111,17 +121,17 @@ struct GenAcc {
             a[i][3] = fmaf(f, nb.z, a[i][3]);
         }
     }
-    UME_DEVI void gather(const float4* list, int len, const float* __restrict__ feat_b) {
+    UME_DEVI void gather(const float4* list, int len, int T, const float* __restrict__ feat_b) {
         const int warp = threadIdx.x >> 5;
         int e = warp;
         for (; e + kNW < len; e += 2 * kNW) {
             const float4 n0 = list[e], n1 = list[e + kNW];
-            add_row(n0, feat_b + (size_t)__float_as_int(n0.w) * C);
-            add_row(n1, feat_b + (size_t)__float_as_int(n1.w) * C);
+            if (__float_as_int(n0.w) <= T) add_row(n0, feat_b + (size_t)__float_as_int(n0.w) * C);   // warp-uniform
+            if (__float_as_int(n1.w) <= T) add_row(n1, feat_b + (size_t)__float_as_int(n1.w) * C);
         }
         for (; e < len; e += kNW) {
             const float4 n0 = list[e];
-            add_row(n0, feat_b + (size_t)__float_as_int(n0.w) * C);
+            if (__float_as_int(n0.w) <= T) add_row(n0, feat_b + (size_t)__float_as_int(n0.w) * C);
         }
     }
     UME_DEVI void store(float4* red_w) {
@@ -135,7 +145,7 @@ struct GenAcc {
 };
 
 template <typename Acc, bool kFma>
-__global__ void __launch_bounds__(kNT, 4) moments_kernel(MomentsParams p) {
+__global__ void __launch_bounds__(kNT, UME_MOMENTS_MINB) moments_kernel(MomentsParams p) {
     extern __shared__ float4 list[];            // cap entries; reused as reduction scratch
     __shared__ CollectSmem sm;
     __shared__ float s_f0[256];
@@ -153,10 +163,10 @@ __global__ void __launch_bounds__(kNT, 4) moments_kernel(MomentsParams p) {
     acc.clear();
     acc.set_channels(C);
 
-    const int used = collect_neighbors<kFma, kNT>(
-        sm, list, p.cap, h, cs, sorted_b, p.grid.N, kx, ky, kz, p.radius, p.K, [&](int len) {
+    const int used = collect_neighbors<kFma, kNT, false>(
+        sm, list, p.cap, h, cs, sorted_b, p.grid.N, kx, ky, kz, p.radius, p.K, [&](int len, int T) {
             __syncthreads();                     // list entries of every warp are visible
-            acc.gather(list, len, feat_b);
+            acc.gather(list, len, T, feat_b);
         });
 
     __syncthreads();                             // everyone is done reading the list

@@ -141,6 +141,61 @@ UME_DEVI void append_hit(CollectSmem& sm, float4* list, int cap, bool hit, float
     }
 }
 
+// ---------------------------------------------------------------- first pass: warp-granular scan + append
+// Every warp takes runs of 32 consecutive candidates that lie inside ONE cell row, so the walk over
+// the rows is warp-uniform (no per-thread search, no divergence) and one shared-memory atomic per 32
+// candidates reserves the slots of the hits.  The next run is loaded before the current one is
+// tested (two 16-byte loads in flight per lane).  Trip counts differ between warps, so nothing in
+// here may synchronise the CTA.
+template <bool kFma, int NT>
+UME_DEVI void scan_append(CollectSmem& sm, float4* list, int cap, const float4* __restrict__ sorted_b, float kx,
+                          float ky, float kz, float r2) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nrows = sm.nrows;
+    int seg = 0, c = warp;                                // cursor: chunk c of run `seg`
+    int seg_len = sm.seg_prefix[1], seg_chunks = (seg_len + 31) >> 5;
+    auto next_run = [&](int& pos, int& cnt) -> bool {
+        while (seg < nrows && c >= seg_chunks) {
+            c -= seg_chunks;
+            ++seg;
+            if (seg < nrows) {
+                seg_len = sm.seg_prefix[seg + 1] - sm.seg_prefix[seg];
+                seg_chunks = (seg_len + 31) >> 5;
+            }
+        }
+        if (seg >= nrows) return false;
+        pos = sm.seg_start[seg] + c * 32;
+        cnt = seg_len - c * 32;
+        c += NW;
+        return true;
+    };
+    int pos, cnt;
+    bool have = (nrows > 0) && next_run(pos, cnt);
+    float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (have && lane < cnt) cur = __ldg(&sorted_b[pos + lane]);
+    while (have) {
+        const int cur_cnt = cnt;
+        int npos, ncnt;
+        const bool have_next = next_run(npos, ncnt);
+        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (have_next && lane < ncnt) nxt = __ldg(&sorted_b[npos + lane]);
+        const float ex = __fsub_rn(cur.x, kx), ey = __fsub_rn(cur.y, ky), ez = __fsub_rn(cur.z, kz);
+        const bool hit = (lane < cur_cnt) && (dist2_ordered<kFma>(ex, ey, ez) < r2);
+        const unsigned m = __ballot_sync(UME_FULL_MASK, hit);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sm.count, __popc(m));
+            base = __shfl_sync(UME_FULL_MASK, base, 0);
+            const int slot = base + __popc(m & lanemask_lt());
+            if (hit && slot < cap) list[slot] = make_float4(ex, ey, ez, cur.w);
+        }
+        cur = nxt;
+        cnt = ncnt;
+        have = have_next;
+    }
+}
+
 // ---------------------------------------------------------------- counting select
 // Given that more than K candidates are in radius, find T = the K-th smallest row index among
 // them.  `each(f)` must call f(row_index) once per in-radius candidate (any thread, any order).
@@ -254,33 +309,37 @@ UME_DEVI int compact_list(CollectSmem& sm, float4* list, int count, int T) {
 }
 
 // ---------------------------------------------------------------- driver
-// Collects the neighbourhood of one query and hands it to `flush(len)` as a dense list of
-// (ex, ey, ez, row index) entries, at most `cap` at a time (`flush` is called once unless the hits
-// overflow the list AND K > cap).  Returns the number of neighbours = min(K, #in radius).
-template <bool kFma, int NT, typename Flush>
+// Collects the neighbourhood of one query and hands it to `flush(len, T)`: list[0..len) holds
+// (ex, ey, ez, row index) entries, of which those with row index <= T are the neighbours
+// (T = INT_MAX when every entry counts).  kCompact = true squeezes the list first so that all `len`
+// entries are neighbours (the ball-query kernel sorts them); kCompact = false leaves the filtering
+// to the consumer (the moment kernel predicates its gather: no extra pass, no barriers).
+// `flush` runs once unless the hits overflow the list AND K > cap.
+// Returns the number of neighbours = min(K, #in radius).
+template <bool kFma, int NT, bool kCompact, typename Flush>
 UME_DEVI int collect_neighbors(CollectSmem& sm, float4* list, int cap, const GridHeader& h,
                                const int* __restrict__ cs, const float4* __restrict__ sorted_b, int N, float kx,
                                float ky, float kz, float radius, int K, Flush flush) {
     const float r2 = __fmul_rn(radius, radius);
     collect_rows<NT>(sm, h, cs, kx, ky, kz, radius);
-    scan_candidates<kFma, NT>(sm, sorted_b, kx, ky, kz, r2,
-                              [&](bool hit, float ex, float ey, float ez, float, int idx) {
-                                  append_hit(sm, list, cap, hit, ex, ey, ez, idx);
-                              });
+    scan_append<kFma, NT>(sm, list, cap, sorted_b, kx, ky, kz, r2);
     __syncthreads();
     const int count = sm.count;
     int shift = 0;
     while (((N - 1) >> shift) >= kHistBins) ++shift;
     if (count <= cap) {
-        int len = count;
+        int len = count, T = 0x7fffffff;
         if (count > K) {
-            const int T = select_kth_index<NT>(sm, K, shift, [&](auto f) {
+            T = select_kth_index<NT>(sm, K, shift, [&](auto f) {
                 for (int i = threadIdx.x; i < count; i += NT) f(__float_as_int(list[i].w));
             });
-            len = compact_list<NT>(sm, list, count, T);
+            if (kCompact) {
+                len = compact_list<NT>(sm, list, count, T);
+                T = 0x7fffffff;
+            }
         }
-        flush(len);
-        return len;
+        flush(len, T);
+        return count > K ? K : count;
     }
     // Overflow: more hits than the list holds.  Everything is recomputed from the candidates.
     int T = 0x7fffffff;
@@ -301,7 +360,7 @@ UME_DEVI int collect_neighbors(CollectSmem& sm, float4* list, int cap, const Gri
                                   const bool acc = hit && idx <= T;
                                   const int n_acc = __syncthreads_count(acc);   // also orders the appends
                                   if (len + n_acc > cap) {
-                                      flush(len);
+                                      flush(len, 0x7fffffff);
                                       __syncthreads();
                                       if (threadIdx.x == 0) sm.count = 0;
                                       __syncthreads();
@@ -311,7 +370,7 @@ UME_DEVI int collect_neighbors(CollectSmem& sm, float4* list, int cap, const Gri
                                   len += n_acc;
                               });
     __syncthreads();
-    flush(len);
+    flush(len, 0x7fffffff);
     return count > K ? K : count;
 }
 
