@@ -81,53 +81,6 @@ def make_workload(wl, seed0):
                             n_kp=wl["n_kp"], model=model)
 
 
-# ----------------------------------------------------------------------------- clocks
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
-                for nm, v in zip(names, f[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
-
-
 # ----------------------------------------------------------------------------- CPU reference leg
 def cpu_reference_pairs(batch, idxs, threads):
     """The oracle's port of evaluate.py:206-257 (fp32, all host threads) on pairs `idxs`."""
@@ -229,7 +182,12 @@ def run_b200(args, wl):
     cnt_s, cnt_t = cnt_s.cpu().numpy(), cnt_t.cpu().numpy()
     bytes_per_launch = 0.5 * (algorithmic_bytes(cnt_s, wl["n_kp"], wl["C"]) + algorithmic_bytes(cnt_t, wl["n_kp"], wl["C"]))
 
-    sampler = ClockSampler(local if world > 1 else 0)
+    from umeregrobust_b200.clocks import ClockSampler
+    try:
+        dev_uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local if world > 1 else 0, uuid=dev_uuid)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
