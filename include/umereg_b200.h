@@ -128,6 +128,39 @@ int ume_knn1_gather_f32(const float* q, const float* p, const float* x, int B, i
                         unsigned flags, int64_t* idx, float* d2, float* out, void* ws, size_t ws_bytes,
                         void* stream);
 
+/* ---------------------------------------------------------------- general K nearest neighbours
+ * Replaces pytorch3d.ops.knn_points as used at utils/loc_utils.py:580,623 (K = 50 self-query, K = 20
+ * cross-query): squared L2, the K smallest in ascending order, lower row index on ties.
+ *   q (B,P1,3), p (B,P2,3) -> idx (B,P1,K) int64 (may be NULL), d2 (B,P1,K) (may be NULL).
+ * Limits: 1 <= K <= min(64, P2). */
+size_t ume_knn_workspace_bytes(int B, int P1, int P2);
+int ume_knn_f32(const float* q, const float* p, int B, int P1, int P2, int K, unsigned flags, int64_t* idx,
+                float* d2, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- hypothesis selection
+ * Replaces utils/loc_utils.py:579-585 `feature_spatial_var(pts, feat, knn)`:
+ *   out[b,i] = mean over the knn-1 nearest other rows j of |feat_i - feat_j|_2.   knn <= 64, C % 4 == 0. */
+size_t ume_feature_spatial_var_workspace_bytes(int B, int N);
+int ume_feature_spatial_var_f32(const float* pts, const float* feat, int B, int N, int C, int knn,
+                                unsigned flags, float* out, void* ws, size_t ws_bytes, void* stream);
+
+/* out[i,:] = (f[i,:] - mean[:]) * w[i]   (utils/loc_utils.py:649-650).  f (rows,C), mean (C), w (rows). */
+int ume_weight_features_f32(const float* f, const float* mean, const float* w, int64_t rows, int C, float* out,
+                            void* stream);
+
+/* Replaces the scoring loop of FeatureCorrelator.feature_corr_hypothesis_test
+ * (utils/loc_utils.py:651-662 -> pc_corr_cost_pytorch3d :621-631 -> pc_corr :592-619) for ALL
+ * hypotheses in one launch (the reference chunks them by `batch`):
+ *   score[h] = (1/Ns) sum_i sum_{k<K} 1/(1 + (|T_h p_i - q_nn|/sigma)^2) <wf_src_i, wf_tgt_nn>
+ * with q_nn the K nearest target rows of the transformed source point.
+ *   src_pts (Ns,3), tgt_pts (Nt,3), wf_src (Ns,C), wf_tgt (Nt,C), T (n_hyp,4,4) row-major
+ *   score (n_hyp), best (1) int64 = arg-max (first index on ties; may be NULL).
+ * Limits: C = 32 or 64, K <= 32. */
+size_t ume_corr_scores_workspace_bytes(int Ns, int Nt, int n_hyp);
+int ume_corr_scores_f32(const float* src_pts, const float* tgt_pts, const float* wf_src, const float* wf_tgt,
+                        const float* T, int Ns, int Nt, int C, int n_hyp, int K, float sigma, unsigned flags,
+                        float* score, int64_t* best, void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- stage profiler
  * When enabled, every stage brackets its kernel launches with CUDA events on the launching
  * stream; ume_profile_read() synchronises those events and returns the accumulated device time
@@ -140,6 +173,7 @@ int ume_knn1_gather_f32(const float* q, const float* p, const float* x, int B, i
 #define UME_PROF_RIGID     4   /* rigid solve                                      */
 #define UME_PROF_BALLQUERY 5
 #define UME_PROF_KNN       6
+#define UME_PROF_CORR      7   /* hypothesis-selection scores                      */
 #define UME_PROF_SLOTS     8
 void ume_profile_enable(int on);
 void ume_profile_reset(void);

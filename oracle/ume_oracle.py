@@ -199,6 +199,56 @@ def ume_kp_layer_forward(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, u
     return T.reshape(bs, n_kp, n_kp, 4, 4), D.reshape(bs, n_kp, n_kp), G, H
 
 
+# ----------------------------------------------------------------------------- hypothesis selection (f1)
+def feature_spatial_var(pts, feat, knn=10, dtype=np.float32, fma=False):
+    """utils/loc_utils.py:579-585: mean over the knn-1 nearest OTHER rows of |f_i - f_j|_2.
+    pts (B,N,3), feat (B,N,C) -> (B,N).  Neighbour search in fp32 (pytorch3d), norms in `dtype`."""
+    nn = p3d.knn_points_c(np.ascontiguousarray(pts, np.float32), np.ascontiguousarray(pts, np.float32), knn, fma=fma)
+    f = feat.astype(dtype)
+    nn_feat = p3d.knn_gather_np(f, nn.idx[:, :, 1:])                       # :581 drops the nearest (the point itself)
+    diff = f[:, :, None, :] - nn_feat
+    return np.sqrt((diff * diff).sum(-1)).mean(-1)
+
+
+def cauchy_kernel(e, k=0.1):
+    """utils/loc_utils.py:588-589."""
+    return 1 / (1 + (e / k) ** 2)
+
+
+def pc_corr_scores(src_pts, tgt_pts, vals_p, vals_q, T, k, sigma, dtype=np.float32, fma=False, chunk=16):
+    """utils/loc_utils.py:621-631 + :592-619 for hypotheses T (n_hyp,4,4):
+    transformed = src @ R^T + t (fp32, like the reference's batched matmul), K nearest target rows
+    (pytorch3d knn, fp32), dist = |p - q| , weight = cauchy(dist; sigma), score = sum w <vp, vq> / Ns."""
+    src32 = np.ascontiguousarray(src_pts, np.float32)
+    tgt32 = np.ascontiguousarray(tgt_pts, np.float32)
+    vp, vq = vals_p.astype(dtype), vals_q.astype(dtype)
+    out = np.empty(len(T), dtype=dtype)
+    for s in range(0, len(T), chunk):
+        Tc = np.asarray(T[s:s + chunk], np.float32)
+        moved = (src32[None] @ np.swapaxes(Tc[:, :3, :3], 1, 2) + Tc[:, None, :3, 3]).astype(np.float32)   # :626
+        nn = p3d.knn_points_c(moved, np.broadcast_to(tgt32[None], (len(Tc),) + tgt32.shape).copy(), k, fma=fma)
+        q = tgt32[nn.idx].astype(dtype)                                         # (c, Ns, k, 3)
+        d = moved.astype(dtype)[:, :, None, :] - q
+        dist = np.sqrt((d * d).sum(-1))                                         # :593
+        w = cauchy_kernel(dist, dtype(sigma))                                   # :596
+        prod = (vp[None, :, None, :] * vq[nn.idx]).sum(-1)                      # :604
+        out[s:s + chunk] = (w * prod).sum(axis=(1, 2)) / dtype(vp.shape[0])     # :613-615
+    return out
+
+
+def feature_corr_hypothesis_test(src_pc, tgt_pc, src_feat, tgt_feat, T_kp, sigma=0.05, corr_num_nn=20,
+                                 dtype=np.float32, fma=False):
+    """utils/loc_utils.py:640-681 `FeatureCorrelator.feature_corr_hypothesis_test` (P=None, no
+    normals): inputs (1,N,3)/(1,N,C)/(n_hyp,4,4).  Returns (best_T (4,4), scores (n_hyp,))."""
+    m = np.concatenate([src_feat, tgt_feat], axis=1).astype(dtype).mean(axis=1)          # :646
+    sw = feature_spatial_var(src_pc, src_feat, knn=50, dtype=dtype, fma=fma)                # :647
+    tw = feature_spatial_var(tgt_pc, tgt_feat, knn=50, dtype=dtype, fma=fma)                # :648
+    wsf = (src_feat.astype(dtype) - m) * sw[..., None]                                      # :649
+    wtf = (tgt_feat.astype(dtype) - m) * tw[..., None]                                      # :650
+    scores = pc_corr_scores(src_pc[0], tgt_pc[0], wsf[0], wtf[0], T_kp, corr_num_nn, sigma, dtype=dtype, fma=fma)
+    return T_kp[int(np.argmax(scores))], scores                                            # :663-681
+
+
 # ----------------------------------------------------------------------------- whole hot path
 def register_pair_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K, radius,
                              dtype=np.float32, fma=False):

@@ -137,6 +137,44 @@ def golden_rigid_random(ref_loc):
     return out
 
 
+def golden_correlator(ref_loc):
+    """FeatureCorrelator.feature_corr_hypothesis_test (utils/loc_utils.py:634-681) plus its parts
+    (feature_spatial_var :579-585, pc_corr_cost_pytorch3d :621-631) on a small pair: 24 hypotheses =
+    the ground truth, perturbed versions of it and random rigid motions."""
+    rng = np.random.default_rng(404)
+    Ns, Nt, C = 1500, 1400, 32
+    src = np.stack([rng.uniform(-15, 15, Ns), rng.uniform(-15, 15, Ns), rng.uniform(-1, 1, Ns)], 1).astype(np.float32)
+    gt = synth.random_rigid(rng, t_range=(2.0, 6.0))
+    sub = rng.choice(Ns, Nt, replace=False)
+    tgt = ((src[sub] + rng.normal(scale=0.03, size=(Nt, 3))).astype(np.float64) @ gt[:3, :3].T + gt[:3, 3]).astype(np.float32)
+    # smooth feature field + noise, so that spatial variance is informative
+    W = rng.normal(size=(3, C)) * 0.15
+    sfeat = synth._normalize_rows(np.sin(src @ W) + 0.2 * rng.normal(size=(Ns, C))).astype(np.float32)
+    tfeat = synth._normalize_rows(sfeat[sub] + 0.05 * rng.normal(size=(Nt, C))).astype(np.float32)
+    hyps = [gt]
+    for i in range(11):
+        d = synth.random_rigid(rng, t_range=(0.0, 0.5 * (i + 1)), max_tilt_deg=2.0, yaw_deg=rng.uniform(-3, 3) * (i + 1))
+        hyps.append(d @ gt)
+    for i in range(12):
+        hyps.append(synth.random_rigid(rng, t_range=(0.0, 10.0)))
+    T_kp = np.stack(hyps).astype(np.float32)
+    corr = ref_loc.FeatureCorrelator(sigma=1.5, batch=8, n_hypotheses=10)
+    with torch.no_grad():
+        best_T = corr.feature_corr_hypothesis_test(t(src)[None], t(tgt)[None], t(sfeat)[None], t(tfeat)[None], t(T_kp))
+        sw = ref_loc.feature_spatial_var(t(src)[None], t(sfeat)[None], knn=50)
+        tw = ref_loc.feature_spatial_var(t(tgt)[None], t(tfeat)[None], knn=50)
+        m = torch.mean(torch.concat((t(sfeat)[None], t(tfeat)[None]), dim=1), dim=1)
+        wsf = (t(sfeat)[None] - m) * sw.unsqueeze(-1)
+        wtf = (t(tfeat)[None] - m) * tw.unsqueeze(-1)
+        scores = ref_loc.pc_corr_cost_pytorch3d(t(T_kp)[:, :3, :3], t(T_kp)[:, :3, 3], t(src), t(tgt), 20, wsf[0], wtf[0], 1.5,
+                                                None, use_norm=False, src_norm=None, tgt_norm=None, dev="cpu")
+    out = dict(src_pts=src, tgt_pts=tgt, src_feat=sfeat, tgt_feat=tfeat, T_kp=T_kp, gt=gt.astype(np.float32),
+               best_T=best_T.numpy(), scores=scores.numpy(), src_var=sw.numpy()[0], tgt_var=tw.numpy()[0],
+               sigma=np.float32(1.5), corr_num_nn=np.int64(20))
+    np.savez_compressed(os.path.join(HERE, "correlator.npz"), **out)
+    return out
+
+
 def main():
     torch.manual_seed(0)
     np.random.seed(0)

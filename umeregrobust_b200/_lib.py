@@ -91,6 +91,13 @@ def _bind(lib):
         "ume_rigid_solve_f32": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
         "ume_knn1_workspace_bytes": (sz, [i32, i32, i32]),
         "ume_knn1_gather_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, u32, vp, vp, vp, vp, sz, vp]),
+        "ume_knn_workspace_bytes": (sz, [i32, i32, i32]),
+        "ume_knn_f32": (i32, [vp, vp, i32, i32, i32, i32, u32, vp, vp, vp, sz, vp]),
+        "ume_feature_spatial_var_workspace_bytes": (sz, [i32, i32]),
+        "ume_feature_spatial_var_f32": (i32, [vp, vp, i32, i32, i32, i32, u32, vp, vp, sz, vp]),
+        "ume_weight_features_f32": (i32, [vp, vp, vp, i64, i32, vp, vp]),
+        "ume_corr_scores_workspace_bytes": (sz, [i32, i32, i32]),
+        "ume_corr_scores_f32": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, u32, vp, vp, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here = header and library out of sync
@@ -104,7 +111,9 @@ EXPORTED_SYMBOLS = ["ume_abi_version", "ume_last_error", "ume_status_string", "u
                     "ume_ball_query_workspace_bytes", "ume_ball_query_f32", "ume_moments_workspace_bytes",
                     "ume_moments_f32", "ume_orthonormalize_f32", "ume_cdist_workspace_bytes", "ume_cdist_f32",
                     "ume_pair_dist_f32", "ume_rigid_solve_f32", "ume_knn1_workspace_bytes",
-                    "ume_knn1_gather_f32"]
+                    "ume_knn1_gather_f32", "ume_knn_workspace_bytes", "ume_knn_f32",
+                    "ume_feature_spatial_var_workspace_bytes", "ume_feature_spatial_var_f32", "ume_weight_features_f32",
+                    "ume_corr_scores_workspace_bytes", "ume_corr_scores_f32"]
 
 
 def lib():
@@ -139,7 +148,7 @@ def launch_count():
     return int(lib().ume_launch_count())
 
 
-PROF_SLOTS = {"grid": 0, "moments": 1, "ortho": 2, "cdist": 3, "rigid": 4, "ball_query": 5, "knn": 6}
+PROF_SLOTS = {"grid": 0, "moments": 1, "ortho": 2, "cdist": 3, "rigid": 4, "ball_query": 5, "knn": 6, "corr": 7}
 
 
 def profile_enable(on=True):

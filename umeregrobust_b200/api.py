@@ -107,14 +107,26 @@ def knn_points(p1, p2, lengths1=None, lengths2=None, norm=2, K=1, version=-1, re
         raise NotImplementedError("knn_points: heterogeneous lengths are not supported")
     if norm != 2:
         raise NotImplementedError("knn_points: only norm=2")
-    if int(K) != 1:
-        raise NotImplementedError("knn_points: only K=1 (evaluate.py:272-275) is on this path")
     p1 = _dev_f32(p1, "p1", 3)
     p2 = _dev_f32(p2, "p2", 3)
     if p1.shape[0] != p2.shape[0]:
         raise ValueError("knn_points: batch sizes differ")
     B, P1, _ = p1.shape
     P2 = p2.shape[1]
+    K = int(K)
+    if K != 1:
+        # general K (utils/loc_utils.py:580,623): sorted ascending, lower row index on ties
+        if K < 1 or K > 64:
+            raise NotImplementedError("knn_points: K must be in [1, 64]")
+        idx = torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
+        d2 = torch.empty((B, P1, K), dtype=torch.float32, device=p1.device)
+        with torch.cuda.device(p1.device):
+            L = _lib.lib()
+            ws = _workspace(L.ume_knn_workspace_bytes(B, P1, P2), p1.device)
+            rc = L.ume_knn_f32(_ptr(p1), _ptr(p2), B, P1, P2, K, _flags(), _ptr(idx), _ptr(d2), _ptr(ws), ws.numel(),
+                               _stream())
+        _lib.check(rc, "knn_points")
+        return _KNN(d2, idx, knn_gather(p2, idx) if return_nn else None)
     idx = torch.empty((B, P1, 1), dtype=torch.int64, device=p1.device)
     d2 = torch.empty((B, P1, 1), dtype=torch.float32, device=p1.device)
     with torch.cuda.device(p1.device):
@@ -373,6 +385,112 @@ class ume_kp_layer(torch.nn.Module):
             D, _, _ = descriptor_cdist(ume_descriptors(G), ume_descriptors(H))
             D = D * (0.707 * 2.0 ** 0.5)                                    # :344 uses 0.707, not 1/sqrt(2)
         return T, D, G.unsqueeze(2).squeeze(), H.unsqueeze(1).squeeze()
+
+
+# ----------------------------------------------------------------------------- hypothesis selection (f1)
+def feature_spatial_var(pts, feat, knn=10):
+    """utils/loc_utils.py:579-585 `feature_spatial_var(pts, feat, knn)`: for every point the mean
+    feature distance to its knn-1 nearest other points.  pts (B,N,3), feat (B,N,C) -> (B,N)."""
+    pts = _dev_f32(pts, "pts", 3)
+    feat = _dev_f32(feat, "feat", 3)
+    B, N, _ = pts.shape
+    C = feat.shape[2]
+    if feat.shape[0] != B or feat.shape[1] != N:
+        raise ValueError("feature_spatial_var: pts %s and feat %s do not agree" % (tuple(pts.shape), tuple(feat.shape)))
+    out = torch.empty((B, N), dtype=torch.float32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        L = _lib.lib()
+        ws = _workspace(L.ume_feature_spatial_var_workspace_bytes(B, N), pts.device)
+        rc = L.ume_feature_spatial_var_f32(_ptr(pts), _ptr(feat), B, N, C, int(knn), _flags(), _ptr(out), _ptr(ws),
+                                           ws.numel(), _stream())
+    _lib.check(rc, "feature_spatial_var")
+    return out
+
+
+def cauchy_kernel(e, k=0.1):
+    """utils/loc_utils.py:588-589."""
+    return 1 / (1 + (e / k) ** 2)
+
+
+def correlation_scores(source_points, target_points, source_vals, target_vals, T, k=20, sigma=0.05):
+    """Scores of ALL hypotheses T (n_hyp,4,4) in one launch: pc_corr_cost_pytorch3d
+    (utils/loc_utils.py:621-631) + pc_corr (:592-619) without the (chunk, Ns, k, C) gathers.
+    source_points (Ns,3), target_points (Nt,3), *_vals (N*,C).  Returns (scores (n_hyp,), best int64 ())."""
+    sp = _dev_f32(source_points, "source_points", 2)
+    tp = _dev_f32(target_points, "target_points", 2)
+    sv = _dev_f32(source_vals, "source_vals", 2)
+    tv = _dev_f32(target_vals, "target_vals", 2)
+    T = _dev_f32(T, "T", 3)
+    Ns, Nt, C, nh = sp.shape[0], tp.shape[0], sv.shape[1], T.shape[0]
+    if sv.shape[0] != Ns or tv.shape[0] != Nt or tv.shape[1] != C or tuple(T.shape[1:]) != (4, 4):
+        raise ValueError("correlation_scores: shapes do not agree")
+    score = torch.empty((nh,), dtype=torch.float32, device=sp.device)
+    best = torch.zeros((), dtype=torch.int64, device=sp.device)
+    with torch.cuda.device(sp.device):
+        L = _lib.lib()
+        ws = _workspace(L.ume_corr_scores_workspace_bytes(Ns, Nt, nh), sp.device)
+        rc = L.ume_corr_scores_f32(_ptr(sp), _ptr(tp), _ptr(sv), _ptr(tv), _ptr(T), Ns, Nt, C, nh, int(k), float(sigma),
+                                   _flags(), _ptr(score), _ptr(best), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "correlation_scores")
+    return score, best
+
+
+def pc_corr_cost_pytorch3d(x1, x2, source_points, target_points, k, source_vals, target_vals, sigma, P=None,
+                           use_norm=False, src_norm=None, tgt_norm=None, dev="cpu"):
+    """utils/loc_utils.py:621-631: scores of the hypotheses (R = x1 (b,3,3), t = x2 (b,3))."""
+    if P is not None or use_norm:
+        raise NotImplementedError("pc_corr_cost_pytorch3d: P / use_norm are never used by the reference's scripts")
+    b = x1.shape[0]
+    T = torch.zeros((b, 4, 4), dtype=torch.float32, device=source_points.device)
+    T[:, :3, :3] = x1
+    T[:, :3, 3] = x2
+    T[:, 3, 3] = 1
+    return correlation_scores(source_points, target_points, source_vals, target_vals, T, k, sigma)[0]
+
+
+def weighted_features(feat, mean, weight):
+    """(feat - mean) * weight[..., None]  (utils/loc_utils.py:649-650); feat (N,C), mean (C,), weight (N,)."""
+    feat = _dev_f32(feat, "feat", 2)
+    mean = _dev_f32(mean, "mean", 1)
+    weight = _dev_f32(weight, "weight", 1)
+    out = torch.empty_like(feat)
+    with torch.cuda.device(feat.device):
+        rc = _lib.lib().ume_weight_features_f32(_ptr(feat), _ptr(mean), _ptr(weight), feat.shape[0], feat.shape[1],
+                                                _ptr(out), _stream())
+    _lib.check(rc, "weighted_features")
+    return out
+
+
+class FeatureCorrelator:
+    """utils/loc_utils.py:634-681, same constructor and `feature_corr_hypothesis_test` signature.
+    `batch` (the reference's chunk size) is accepted and ignored: all hypotheses are scored by one
+    launch."""
+
+    def __init__(self, n_clusters=8, batch=1, n_hypotheses=1, sigma=0.05, P=None, corr_num_nn=20):
+        self.n_clusters = n_clusters
+        self.batch = batch
+        self.sigma = sigma
+        self.n_hypotheses = n_hypotheses
+        self.P = P
+        self.corr_num_nn = corr_num_nn
+
+    def scores(self, source_pc, target_pc, source_feat, target_feat, T_kp):
+        """Scores of every hypothesis (the `mmf_score` of :663) and the index of the best."""
+        if self.P is not None:
+            raise NotImplementedError("FeatureCorrelator: P is never set by the reference's scripts")
+        # :646 mean feature over both clouds (a C-vector; one torch reduction)
+        m = torch.mean(torch.cat((source_feat, target_feat), dim=1), dim=1)[0]
+        src_w = feature_spatial_var(source_pc, source_feat, knn=50)[0]          # :647
+        tgt_w = feature_spatial_var(target_pc, target_feat, knn=50)[0]          # :648
+        wsf = weighted_features(source_feat[0], m, src_w)                        # :649
+        wtf = weighted_features(target_feat[0], m, tgt_w)                        # :650
+        return correlation_scores(source_pc[0], target_pc[0], wsf, wtf, T_kp, self.corr_num_nn, self.sigma)
+
+    def feature_corr_hypothesis_test(self, source_pc, target_pc, source_feat, target_feat, T_kp, src_norm=None,
+                                     tgt_norm=None):
+        """source_pc (1,Ns,3), target_pc (1,Nt,3), *_feat (1,N*,C), T_kp (n_hyp,4,4) -> best T (4,4)."""
+        score, best = self.scores(source_pc, target_pc, source_feat, target_feat, T_kp)
+        return T_kp[best]
 
 
 # ----------------------------------------------------------------------------- fused hot path

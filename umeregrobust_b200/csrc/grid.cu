@@ -47,7 +47,7 @@ __global__ void grid_bbox_kernel(const float* __restrict__ q, int nq, int* __res
 }
 
 __global__ void grid_params_kernel(const int* __restrict__ bbox, GridHeader* __restrict__ hdr, int B,
-                                   float expand, float cell, int cells_cap) {
+                                   float expand, float cell, int cells_cap, int N) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     GridHeader h;
@@ -80,7 +80,13 @@ __global__ void grid_params_kernel(const int* __restrict__ bbox, GridHeader* __r
     }
     float emax = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
     float s = cell;
-    if (!(s > 0.f)) {
+    if (s < 0.f) {
+        // automatic, about -cell points per cell for a surface-like (planar) cloud of N points
+        const float fl = emax * 1e-3f;
+        float e0 = fmaxf(ext[0], fl), e1 = fmaxf(ext[1], fl), e2 = fmaxf(ext[2], fl);
+        const float emin = fminf(e0, fminf(e1, e2));
+        s = sqrtf(e0 * e1 * e2 / emin * (-cell) / (float)max(N, 1));
+    } else if (!(s > 0.f)) {
         // automatic: the finest grid the table allows (the loop below coarsens it until it fits)
         const float fl = emax * 1e-3f;
         s = cbrtf(fmaxf(ext[0], fl) * fmaxf(ext[1], fl) * fmaxf(ext[2], fl) / (float)cells_cap);
@@ -252,7 +258,7 @@ int grid_build(const float* pts, const float* q, int B, int N, int nq, float exp
         dim3 g((unsigned)min((nq + 255) / 256, 64), (unsigned)B);
         grid_bbox_kernel<<<g, 256, 0, stream>>>(q, nq, bbox);
     }
-    grid_params_kernel<<<(B + 127) / 128, 128, 0, stream>>>(bbox, hdr, B, expand, cell, cells_cap);
+    grid_params_kernel<<<(B + 127) / 128, 128, 0, stream>>>(bbox, hdr, B, expand, cell, cells_cap, N);
     cudaMemsetAsync(g_count, 0, (size_t)B * cells_cap * sizeof(int), stream);
     // CTAs per cloud: about two waves of the 148 SMs in total, at least ~2048 points per CTA
     int G = (4 * 148) / B;

@@ -116,8 +116,8 @@ UME_DEVI unsigned lanemask_lt() {
 // Host entry points implemented in grid.cu
 size_t grid_workspace_bytes(int B, int N, int cells_cap);
 // Builds the grid for clouds `pts` (B,N,3) over the bounding box of `q` (B,nq,3) grown by
-// `expand`; cell size `cell` (<= 0: the finest the table allows).  Carves its buffers out of `ws`
-// and fills `view`.
+// `expand`; cell size `cell` (0: the finest the table allows; < 0: about -cell points per cell for
+// a surface-like cloud).  Carves its buffers out of `ws` and fills `view`.
 int grid_build(const float* pts, const float* q, int B, int N, int nq, float expand, float cell,
                int cells_cap, Workspace& ws, GridView* view, cudaStream_t stream);
 

@@ -10,7 +10,9 @@ import sys
 from . import api
 
 _NAMES = ("ball_query", "knn_points", "knn_gather", "my_ume_generation", "ume_cdist",
-          "batch_estimate_transform_ume_old", "ume_kp_layer", "ball_query_gather")
+          "batch_estimate_transform_ume_old", "ume_kp_layer", "ball_query_gather",
+          # hypothesis selection
+          "FeatureCorrelator", "feature_spatial_var", "cauchy_kernel", "pc_corr_cost_pytorch3d")
 
 
 def patch_reference(evaluate_module=None, loc_utils_module=None):
