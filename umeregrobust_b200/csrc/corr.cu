@@ -43,25 +43,84 @@ UME_DEVI void topk_insert(float (&bd)[KMAX], int (&bj)[KMAX], int& n, int K, flo
     if (n < K) ++n;
 }
 
+// K best in a per-thread array (local memory), any K <= KMAX.
+template <int KMAX>
+struct ArrayTopK {
+    float bd[KMAX];
+    int bj[KMAX];
+    int n, K;
+    UME_DEVI void reset(int k) { n = 0; K = k; }
+    UME_DEVI bool full() const { return n == K; }
+    UME_DEVI float worst() const { return bd[K - 1]; }
+    UME_DEVI int size() const { return n; }
+    UME_DEVI void consider(float d, int j) { topk_insert<KMAX>(bd, bj, n, K, d, j); }
+    template <typename F>
+    UME_DEVI void for_each(F f) const {
+        for (int k = 0; k < n; ++k) f(bd[k], bj[k]);
+    }
+};
+
+// K best in REGISTERS (K is a compile-time constant): sorted ascending, empty slots hold +inf.
+// Insertion is one fully unrolled carry pass — no local memory, no data-dependent loop.
+template <int K_>
+struct RegTopK {
+    float bd[K_];
+    int bj[K_];
+    UME_DEVI void reset(int) {
+#pragma unroll
+        for (int k = 0; k < K_; ++k) { bd[k] = INFINITY; bj[k] = 0x7fffffff; }
+    }
+    UME_DEVI bool full() const { return bj[K_ - 1] != 0x7fffffff; }
+    UME_DEVI float worst() const { return bd[K_ - 1]; }
+    UME_DEVI void consider(float d, int j) {
+        if (!(d < bd[K_ - 1] || (d == bd[K_ - 1] && j < bj[K_ - 1]))) return;
+#pragma unroll
+        for (int k = 0; k < K_; ++k) {
+            const bool lt = d < bd[k] || (d == bd[k] && j < bj[k]);
+            const float td = lt ? bd[k] : d;
+            const int tj = lt ? bj[k] : j;
+            bd[k] = lt ? d : bd[k];
+            bj[k] = lt ? j : bj[k];
+            d = td;
+            j = tj;
+        }
+    }
+    template <typename F>
+    UME_DEVI void for_each(F f) const {
+#pragma unroll
+        for (int k = 0; k < K_; ++k)
+            if (bj[k] != 0x7fffffff) f(bd[k], bj[k]);          // fewer than K rows in the cloud: empty slots
+    }
+};
+
 // Exact K nearest rows of one cloud for query (qx,qy,qz).  dist2 in pytorch3d's arithmetic.
-template <int KMAX, bool kFma>
+template <bool kFma, typename Top>
 UME_DEVI void grid_knn(const GridHeader& h, const int* __restrict__ cs, const float4* __restrict__ sorted_b,
-                       float qx, float qy, float qz, int K, float (&bd)[KMAX], int (&bj)[KMAX], int& n) {
-    n = 0;
+                       float qx, float qy, float qz, Top& top) {
     const int cx = cell_coord(qx, h.ox, h.inv_s, h.nx), cy = cell_coord(qy, h.oy, h.inv_s, h.ny),
               cz = cell_coord(qz, h.oz, h.inv_s, h.nz);
     const int max_ring = max(h.nx, max(h.ny, h.nz));
+    // squared distance from the query to the grid's box (0 inside): every row is at least that far
+    const float ox = fmaxf(fmaxf(h.ox - qx, qx - h.hx), 0.f), oy = fmaxf(fmaxf(h.oy - qy, qy - h.hy), 0.f),
+                oz = fmaxf(fmaxf(h.oz - qz, qz - h.hz), 0.f);
+    const float out2 = (ox * ox + oy * oy + oz * oz) * 0.9999f;
     for (int ring = 0; ring <= max_ring; ++ring) {
-        if (ring >= 2 && n == K) {
-            // every row not yet visited lies in a cell at Chebyshev distance >= ring, i.e. at least
-            // (ring - 1) * s away from the query
+        if (ring >= 1 && top.full()) {
+            // A row not yet visited lies in a cell at Chebyshev distance >= ring from the (clamped)
+            // centre cell: along that axis it is >= (ring-1)*s + (query's overshoot on that axis) away,
+            // along the others >= the overshoot, hence dist^2 >= ((ring-1)*s)^2 + |overshoot|^2.
+            // Far-away queries (bad hypotheses) therefore stop after a few rings too.
             const float lb = (float)(ring - 1) * h.s * 0.9999f;
-            if (bd[K - 1] < lb * lb) break;
+            if (top.worst() < lb * lb + out2) break;
         }
         const int z0 = max(cz - ring, 0), z1 = min(cz + ring, h.nz - 1);
         const int y0 = max(cy - ring, 0), y1 = min(cy + ring, h.ny - 1);
         for (int iz = z0; iz <= z1; ++iz) {
             const bool zshell = (iz - cz == ring) || (cz - iz == ring);
+            // distance from the query to the slab of cell layer iz (slightly under-estimated)
+            const float zlo = h.oz + (float)iz * h.s, zhi = zlo + h.s;
+            const float dz = fmaxf(fmaxf(zlo - qz, qz - zhi), 0.f) * 0.9999f;
+            if (top.full() && dz * dz >= top.worst()) continue;
             for (int iy = y0; iy <= y1; ++iy) {
                 const bool shell = zshell || (iy - cy == ring) || (cy - iy == ring);
                 const int base = (iz * h.ny + iy) * h.nx;
@@ -73,12 +132,24 @@ UME_DEVI void grid_knn(const GridHeader& h, const int* __restrict__ cs, const fl
                     if (cx - ring >= 0) { xa[nr] = xb[nr] = cx - ring; ++nr; }
                     if (cx + ring <= h.nx - 1) { xa[nr] = xb[nr] = cx + ring; ++nr; }
                 }
+                if (top.full()) {
+                    // prune by the distance from the query to the cell row's box: nothing farther than the
+                    // current K-th best can enter the list; on full rows also trim the x range
+                    const float ylo = h.oy + (float)iy * h.s, yhi = ylo + h.s;
+                    const float dy = fmaxf(fmaxf(ylo - qy, qy - yhi), 0.f) * 0.9999f;
+                    const float rem = top.worst() - dz * dz - dy * dy;
+                    if (rem <= 0.f) continue;
+                    const float half = sqrtf(rem) * 1.0001f + h.s * 1e-3f;
+                    const int tx0 = cell_coord(qx - half, h.ox, h.inv_s, h.nx), tx1 = cell_coord(qx + half, h.ox, h.inv_s, h.nx);
+                    for (int r = 0; r < nr; ++r) { xa[r] = max(xa[r], tx0); xb[r] = min(xb[r], tx1); }
+                }
                 for (int r = 0; r < nr; ++r) {
+                    if (xb[r] < xa[r]) continue;
                     const int s = __ldg(&cs[base + xa[r]]), e = __ldg(&cs[base + xb[r] + 1]);
                     for (int t = s; t < e; ++t) {
                         const float4 c = __ldg(&sorted_b[t]);
                         const float d = dist2_ordered<kFma>(__fsub_rn(qx, c.x), __fsub_rn(qy, c.y), __fsub_rn(qz, c.z));
-                        topk_insert<KMAX>(bd, bj, n, K, d, __float_as_int(c.w));
+                        top.consider(d, __float_as_int(c.w));
                     }
                 }
             }
@@ -97,12 +168,12 @@ __global__ void __launch_bounds__(128) knn_kernel(GridView grid, const float* __
     const int* cs = grid.cell_start + (size_t)b * (grid.cells_cap + 1);
     const float4* sorted_b = grid.sorted + (size_t)b * grid.N;
     const size_t qo = (size_t)b * P1 + i;
-    float bd[KMAX];
-    int bj[KMAX], n;
-    grid_knn<KMAX, kFma>(h, cs, sorted_b, q[qo * 3 + 0], q[qo * 3 + 1], q[qo * 3 + 2], K, bd, bj, n);
+    ArrayTopK<KMAX> top;
+    top.reset(K);
+    grid_knn<kFma>(h, cs, sorted_b, q[qo * 3 + 0], q[qo * 3 + 1], q[qo * 3 + 2], top);
     for (int k = 0; k < K; ++k) {
-        if (idx) idx[qo * K + k] = (k < n) ? bj[k] : 0;
-        if (d2) d2[qo * K + k] = (k < n) ? bd[k] : 0.f;
+        if (idx) idx[qo * K + k] = (k < top.n) ? top.bj[k] : 0;
+        if (d2) d2[qo * K + k] = (k < top.n) ? top.bd[k] : 0.f;
     }
 }
 
@@ -121,14 +192,14 @@ __global__ void __launch_bounds__(128) spatial_var_kernel(GridView grid, const f
     const float4* sorted_b = grid.sorted + (size_t)b * N;
     const float4 me = sorted_b[t];                           // cell order: neighbouring threads, neighbouring points
     const int i = __float_as_int(me.w);
-    float bd[KMAX];
-    int bj[KMAX], n;
-    grid_knn<KMAX, kFma>(h, cs, sorted_b, me.x, me.y, me.z, K, bd, bj, n);
+    ArrayTopK<KMAX> top;
+    top.reset(K);
+    grid_knn<kFma>(h, cs, sorted_b, me.x, me.y, me.z, top);
     const float* fb = feat + (size_t)b * N * C;
     const float* fi = fb + (size_t)i * C;
     float acc = 0.f;
-    for (int k = 1; k < n; ++k) {
-        const float* fj = fb + (size_t)bj[k] * C;
+    for (int k = 1; k < top.n; ++k) {
+        const float* fj = fb + (size_t)top.bj[k] * C;
         float s = 0.f;
         for (int c = 0; c < C; c += 4) {
             const float4 a = ldg_f4(fi + c), v = ldg_f4(fj + c);
@@ -167,7 +238,7 @@ struct CorrParams {
     float inv_sigma;
 };
 
-template <int C4, int KMAX, bool kFma>
+template <int C4, typename Top, bool kFma>
 __global__ void __launch_bounds__(kCorrThreads) corr_score_kernel(CorrParams p) {
     __shared__ float s_red[kCorrThreads / 32];
     const GridHeader hs = p.src_grid.hdr[0];
@@ -195,20 +266,20 @@ __global__ void __launch_bounds__(kCorrThreads) corr_score_kernel(CorrParams p) 
             const float qx = fmaf(me.z, __ldg(T + 2), fmaf(me.y, __ldg(T + 1), me.x * __ldg(T + 0))) + __ldg(T + 3);
             const float qy = fmaf(me.z, __ldg(T + 6), fmaf(me.y, __ldg(T + 5), me.x * __ldg(T + 4))) + __ldg(T + 7);
             const float qz = fmaf(me.z, __ldg(T + 10), fmaf(me.y, __ldg(T + 9), me.x * __ldg(T + 8))) + __ldg(T + 11);
-            float bd[KMAX];
-            int bj[KMAX], n;
-            grid_knn<KMAX, kFma>(ht, cs, tgt_sorted, qx, qy, qz, p.K, bd, bj, n);
-            for (int k = 0; k < n; ++k) {
-                const float* row = p.wf_tgt + (size_t)bj[k] * (C4 * 4);
+            Top top;
+            top.reset(p.K);
+            grid_knn<kFma>(ht, cs, tgt_sorted, qx, qy, qz, top);
+            top.for_each([&](float dk, int jk) {
+                const float* row = p.wf_tgt + (size_t)jk * (C4 * 4);
                 float v = 0.f;
 #pragma unroll
                 for (int c = 0; c < C4; ++c) {
                     const float4 g = ldg_f4(row + 4 * c);
                     v = fmaf(sf[c].x, g.x, v); v = fmaf(sf[c].y, g.y, v); v = fmaf(sf[c].z, g.z, v); v = fmaf(sf[c].w, g.w, v);
                 }
-                const float e = sqrtf(bd[k]) * p.inv_sigma;          // |p - q| / sigma
+                const float e = sqrtf(dk) * p.inv_sigma;             // |p - q| / sigma
                 acc = fmaf(v, 1.f / fmaf(e, e, 1.f), acc);            // cauchy_kernel (:588-589)
-            }
+            });
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(UME_FULL_MASK, acc, o);
@@ -251,6 +322,22 @@ __global__ void __launch_bounds__(256) corr_finalize_kernel(const float* __restr
     if (threadIdx.x == 0 && best) *best = (s_i[0] == 0x7fffffff) ? 0 : s_i[0];
 }
 
+// K = 20 (the reference's corr_num_nn) keeps the K best in registers; other K use the array version.
+template <int C4, bool kFma>
+void launch_corr_c(const CorrParams& p, int K, dim3 grid, cudaStream_t stream) {
+    if (K == 20) corr_score_kernel<C4, RegTopK<20>, kFma><<<grid, kCorrThreads, 0, stream>>>(p);
+    else corr_score_kernel<C4, ArrayTopK<32>, kFma><<<grid, kCorrThreads, 0, stream>>>(p);
+}
+void launch_corr(const CorrParams& p, int C, int K, bool fma, dim3 grid, cudaStream_t stream) {
+    if (C == 32) {
+        if (fma) launch_corr_c<8, true>(p, K, grid, stream);
+        else launch_corr_c<8, false>(p, K, grid, stream);
+    } else {
+        if (fma) launch_corr_c<16, true>(p, K, grid, stream);
+        else launch_corr_c<16, false>(p, K, grid, stream);
+    }
+}
+
 template <bool kFma>
 int launch_knn(const GridView& g, const float* q, int B, int P1, int K, int64_t* idx, float* d2, cudaStream_t stream) {
     dim3 grid((unsigned)((P1 + 127) / 128), (unsigned)B);
@@ -284,7 +371,7 @@ extern "C" int ume_knn_f32(const float* q, const float* pcl, int B, int P1, int 
     UME_REQUIRE(ws && ws_bytes >= ume_knn_workspace_bytes(B, P1, P2), UME_ERR_WORKSPACE, "ume_knn_f32: workspace too small");
     Workspace w(ws, ws_bytes);
     GridView g;
-    int rc = grid_build(pcl, pcl, B, P2, P2, 0.f, -(float)max(4, K / 2), kCellsCap, w, &g, stream);
+    int rc = grid_build(pcl, pcl, B, P2, P2, 0.f, -(float)max(2, K / 8), kCellsCap, w, &g, stream);
     if (rc != UME_OK) return rc;
     ProfScope prof(UME_PROF_KNN, stream);
     return (flags & UME_FLAG_FMA_DIST) ? launch_knn<true>(g, q, B, P1, K, idx, d2, stream)
@@ -310,7 +397,7 @@ extern "C" int ume_feature_spatial_var_f32(const float* pts, const float* feat, 
                 "ume_feature_spatial_var_f32: workspace too small");
     Workspace w(ws, ws_bytes);
     GridView g;
-    int rc = grid_build(pts, pts, B, N, N, 0.f, -(float)max(4, knn / 2), kCellsCap, w, &g, stream);
+    int rc = grid_build(pts, pts, B, N, N, 0.f, -(float)max(2, knn / 8), kCellsCap, w, &g, stream);
     if (rc != UME_OK) return rc;
     ProfScope prof(UME_PROF_KNN, stream);
     cudaMemsetAsync(out, 0, (size_t)B * N * sizeof(float), stream);      // rows with non-finite coordinates
@@ -361,7 +448,7 @@ extern "C" int ume_corr_scores_f32(const float* src_pts, const float* tgt_pts, c
     CorrParams p;
     int rc = grid_build(src_pts, src_pts, 1, Ns, Ns, 0.f, -8.f, kCellsCap, w, &p.src_grid, stream);
     if (rc != UME_OK) return rc;
-    rc = grid_build(tgt_pts, tgt_pts, 1, Nt, Nt, 0.f, -(float)max(4, K / 2), kCellsCap, w, &p.tgt_grid, stream);
+    rc = grid_build(tgt_pts, tgt_pts, 1, Nt, Nt, 0.f, -(float)max(2, K / 8), kCellsCap, w, &p.tgt_grid, stream);
     if (rc != UME_OK) return rc;
     const int nb = (Ns + kCorrThreads - 1) / kCorrThreads;
     p.partial = w.take<float>((size_t)n_hyp * nb);
@@ -373,13 +460,7 @@ extern "C" int ume_corr_scores_f32(const float* src_pts, const float* tgt_pts, c
     dim3 grid((unsigned)nb, (unsigned)gy);
     const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
     ProfScope prof(UME_PROF_CORR, stream);
-    if (C == 32) {
-        if (fma) corr_score_kernel<8, 32, true><<<grid, kCorrThreads, 0, stream>>>(p);
-        else corr_score_kernel<8, 32, false><<<grid, kCorrThreads, 0, stream>>>(p);
-    } else {
-        if (fma) corr_score_kernel<16, 32, true><<<grid, kCorrThreads, 0, stream>>>(p);
-        else corr_score_kernel<16, 32, false><<<grid, kCorrThreads, 0, stream>>>(p);
-    }
+    launch_corr(p, C, K, fma, grid, stream);
     corr_finalize_kernel<<<1, 256, 0, stream>>>(p.partial, n_hyp, nb, 1.f / (float)Ns, score, best);
     count_launch(2);
     return check_launch("corr_score_kernel");
