@@ -71,6 +71,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-pairs", type=int, default=24)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--graph", type=int, default=None, help="replay the step from a CUDA graph (default: on for <= 8 pairs)")
     return ap.parse_args()
 
 
@@ -161,8 +162,10 @@ def run_b200(args, wl):
     eng = RegistrationEngine(K=K_NN, radius=RADIUS, device=dev, want_D=True)
     pairs = wl["pairs"]
 
+    use_graph = (pairs <= 8) if args.graph is None else bool(args.graph)
+
     def step():
-        out = eng.register(batch)
+        out = eng.register_graphed(batch) if use_graph else eng.register(batch)
         if world > 1:
             out = gather_results(out)
         return out
@@ -268,7 +271,7 @@ def run_b200(args, wl):
         "config": {"workload": args.workload, "pairs_per_gpu_per_step": pairs, "points": wl["N"],
                    "keypoints": wl["n_kp"], "channels": wl["C"], "K": K_NN, "radius": RADIUS,
                    "mean_neighbours": float(0.5 * (cnt_s.mean() + cnt_t.mean())),
-                   "cdist_impl": ume.config["cdist_impl"], "cell_div2": ume.config["cell_div2"],
+                   "cdist_impl": ume.config["cdist_impl"], "cell_div2": ume.config["cell_div2"], "cuda_graph": use_graph,
                    "l2_policy": "inputs (%.1f GB per step) exceed the 126 MB L2" % (h2d / 1e9),
                    "parallelism": "pairs sharded over %d GPU(s), one all-gather of results per step" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -100,3 +100,26 @@ def test_end_to_end_pair_registration_recovers_ground_truth(ume):
     ref_sc = orc.feature_corr_hypothesis_test(p["src_pts"][None][:, ss], p["tgt_pts"][None][:, ts], p["src_feat"][None][:, ss],
                                               p["tgt_feat"][None][:, ts], host(T)[top], sigma=1.5, corr_num_nn=20)[1]
     assert np.abs(ref_sc - sc[top]).max() < 2e-4 * np.abs(sc[top]).max()
+
+
+def test_weighted_match_subsample_distribution(ume):
+    # evaluate.py:233-245 semantics: without replacement, P(first pick = i) = p_i; inclusion frequencies
+    # match numpy's sampler statistically (bit parity with numpy's stream is impossible by construction)
+    rng = np.random.default_rng(0)
+    d = rng.uniform(0.0, 1.0, 64).astype(np.float32)
+    tau, k, trials = 0.25, 16, 4000
+    a = np.exp((1 - d) / tau)
+    p = a / a.sum()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    D = dev(np.tile(d, (trials, 1)))
+    idx = host(ume.weighted_match_subsample(D, tau, k, generator=g))
+    assert idx.shape == (trials, k)
+    assert all(len(set(r)) == k for r in idx[:50])                      # no repeats
+    freq = np.bincount(idx.ravel(), minlength=64) / trials
+    ref = np.zeros(64)
+    for _ in range(trials):
+        ref[rng.choice(64, k, replace=False, p=p)] += 1
+    ref /= trials
+    assert np.abs(freq - ref).max() < 0.05
+    one = ume.weighted_match_subsample(dev(d), tau, 100)
+    assert one.shape == (64,) and sorted(host(one).tolist()) == list(range(64))   # k > n: everything

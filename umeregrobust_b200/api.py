@@ -493,6 +493,25 @@ class FeatureCorrelator:
         return T_kp[best]
 
 
+# ----------------------------------------------------------------------------- match sub-sampling (f2)
+def weighted_match_subsample(ume_d, tau, num_samples, generator=None):
+    """Device-side equivalent of evaluate.py:233-245: draw `num_samples` of the n matches WITHOUT
+    replacement with probability proportional to exp((1 - d) / tau).  The reference does this on
+    the host with np.random.choice (a D2H sync per pair); here it is the Gumbel-top-k trick on the
+    device — the same distribution (successive sampling without replacement == top-k of
+    log-weight + Gumbel noise), but not the same random stream, so parity tests feed `cond` in as
+    data.  ume_d (n,) or (B,n) -> int64 indices (num_samples,) or (B,num_samples), unordered like
+    np.random.choice's result.  Uses torch's RNG and top-k (glue between two kernels of the path,
+    not a measured stage)."""
+    d = ume_d if ume_d.dim() == 2 else ume_d[None]
+    k = min(int(num_samples), d.shape[-1])
+    logw = (1.0 - d.float()) / float(tau)
+    u = torch.rand(d.shape, device=d.device, generator=generator).clamp_(min=1e-20, max=1.0 - 1e-7)
+    keys = logw - torch.log(-torch.log(u))
+    idx = torch.topk(keys, k, dim=-1, sorted=False).indices
+    return idx if ume_d.dim() == 2 else idx[0]
+
+
 # ----------------------------------------------------------------------------- fused hot path
 def register_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K, radius, want_D=False,
                         centered=True, buf=None):

@@ -29,6 +29,7 @@ class RegistrationEngine:
         self._staging = {}
         self._host_out = {}
         self._arena = {}                 # outputs of register(): reused every call
+        self._graphs = {}                # CUDA graphs of register(), keyed on input addresses / shapes
         self._chunk_arena = [{}, {}]     # per-stream outputs of register_host()
 
     # ------------------------------------------------------------------ device-resident batch
@@ -40,6 +41,27 @@ class RegistrationEngine:
         return api.register_hypotheses(batch["src_pts"], batch["src_feat"], batch["src_kp"], batch["tgt_pts"],
                                        batch["tgt_feat"], batch["tgt_kp"], self.K, self.radius, want_D=self.want_D,
                                        centered=self.centered, buf=self._arena)
+
+    def register_graphed(self, batch):
+        """Same as `register`, replayed from a CUDA graph: the ~25 launches of a step (grid build,
+        moments, descriptors, distance GEMM, solve, for both clouds) become one graph launch, which
+        matters for small batches (a single pair is launch-latency bound).  The graph is keyed on
+        the input tensors' addresses and shapes — refill the same buffers between calls; new
+        buffers trigger a new capture."""
+        key = tuple((batch[k].data_ptr(), tuple(batch[k].shape)) for k in _IN_KEYS) + \
+            (self.K, self.radius, self.want_D, self.centered, tuple(sorted(api.config.items(), key=str)))
+        entry = self._graphs.get(key)
+        if entry is None:
+            with torch.cuda.device(self.device):
+                self.register(batch)                      # warm-up: arena, function attributes
+                torch.cuda.synchronize(self.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self.register(batch)
+            entry = (graph, out)
+            self._graphs[key] = entry
+        entry[0].replay()
+        return entry[1]
 
     # ------------------------------------------------------------------ host-resident batch
     def _stage(self, slot, key, shape, dtype):
