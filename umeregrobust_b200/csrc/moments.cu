@@ -13,10 +13,18 @@ namespace ume {
 
 namespace {
 
-constexpr int kNT = 256;
-#ifndef UME_MOMENTS_MINB
-#define UME_MOMENTS_MINB 4
+// Tunables (kernel-variant experiments build with -D overrides; the defaults are the measured best)
+#ifndef UME_MOMENTS_NT
+#define UME_MOMENTS_NT 256        // threads per keypoint CTA
 #endif
+#ifndef UME_MOMENTS_MINB
+#define UME_MOMENTS_MINB 5        // CTAs per SM the register allocation is capped for
+#endif
+#ifndef UME_GATHER_UNROLL
+#define UME_GATHER_UNROLL 2       // feature-row loads in flight per lane
+#endif
+constexpr int kNT = UME_MOMENTS_NT;
+constexpr int kGU = UME_GATHER_UNROLL;
 constexpr int kNW = kNT / 32;
 
 struct MomentsParams {
@@ -35,24 +43,30 @@ template <int LPR>
 struct VecAcc {
     static constexpr int C = 4 * LPR;
     static constexpr int RPW = 32 / LPR;       // feature rows per warp instruction
-    float a[4][4];                             // [channel within lane][moment 1,x,y,z]
+    // accumulators as packed pairs for Blackwell's two-wide fp32 pipe (FADD2 / FFMA2):
+    // a01[j] = moment j of channels (0,1), a23[j] = channels (2,3); moments j = 1, x, y, z
+    float2 a01[4], a23[4];
 
     UME_DEVI void set_channels(int) {}
     UME_DEVI void clear() {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) { a01[j] = make_float2(0.f, 0.f); a23[j] = make_float2(0.f, 0.f); }
     }
+    static UME_DEVI void fma2(float2& acc, const float2& x, const float2& y) {
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(reinterpret_cast<uint64_t&>(acc))
+            : "l"(reinterpret_cast<const uint64_t&>(x)), "l"(reinterpret_cast<const uint64_t&>(y)));
+    }
+    static UME_DEVI void add2(float2& acc, const float2& x) {
+        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(reinterpret_cast<uint64_t&>(acc)) : "l"(reinterpret_cast<const uint64_t&>(x)));
+    }
+    // 2 FADD2 + 6 FFMA2 per feature float4 (16 scalar fp32 operations)
     UME_DEVI void add(const float4& nb, const float4& f) {
-        const float fv[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            a[i][0] += fv[i];
-            a[i][1] = fmaf(fv[i], nb.x, a[i][1]);
-            a[i][2] = fmaf(fv[i], nb.y, a[i][2]);
-            a[i][3] = fmaf(fv[i], nb.z, a[i][3]);
-        }
+        const float2 f01 = make_float2(f.x, f.y), f23 = make_float2(f.z, f.w);
+        const float2 nx = make_float2(nb.x, nb.x), ny = make_float2(nb.y, nb.y), nz = make_float2(nb.z, nb.z);
+        add2(a01[0], f01); add2(a23[0], f23);
+        fma2(a01[1], f01, nx); fma2(a23[1], f23, nx);
+        fma2(a01[2], f01, ny); fma2(a23[2], f23, ny);
+        fma2(a01[3], f01, nz); fma2(a23[3], f23, nz);
     }
     // entries whose row index exceeds T are not neighbours: their load is predicated off and they
     // contribute zeros
@@ -63,17 +77,17 @@ struct VecAcc {
         const float* fl = feat_b + 4 * l;
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
         int e = warp * RPW + sub;
-        for (; e + 3 * stride < len; e += 4 * stride) {
-            float4 nb[4], f[4];
+        for (; e + (kGU - 1) * stride < len; e += kGU * stride) {
+            float4 nb[kGU], f[kGU];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) nb[u] = list[e + u * stride];
+            for (int u = 0; u < kGU; ++u) nb[u] = list[e + u * stride];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kGU; ++u) {
                 const int j = __float_as_int(nb[u].w);
                 f[u] = (j <= T) ? ldg_f4(fl + (size_t)j * C) : zero;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) add(nb[u], f[u]);
+            for (int u = 0; u < kGU; ++u) add(nb[u], f[u]);
         }
         for (; e < len; e += stride) {
             const float4 nb = list[e];
@@ -83,6 +97,9 @@ struct VecAcc {
     }
     // combine the RPW row groups of the warp, then lanes [0,LPR) hold the warp's C x 4 partial
     UME_DEVI void store(float4* red_w) {
+        float a[4][4];                         // [channel within lane][moment]
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a[0][j] = a01[j].x; a[1][j] = a01[j].y; a[2][j] = a23[j].x; a[3][j] = a23[j].y; }
 #pragma unroll
         for (int o = LPR; o < 32; o <<= 1)
 #pragma unroll

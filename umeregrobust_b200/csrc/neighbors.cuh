@@ -13,7 +13,7 @@ namespace ume {
 
 static constexpr int kMaxRows = 64;       // (2*div+2)^2 <= 36 cell rows per query
 static constexpr int kHistBins = 512;
-static constexpr int kBitmapWords = 512;  // bin width <= 16384 indices  ->  N <= 512*16384
+static constexpr int kBitmapWords = 128;  // bin width <= 4096 indices  ->  N <= 512*4096 (= 2 M points per cloud)
 
 struct CollectSmem {
     int seg_start[kMaxRows];
