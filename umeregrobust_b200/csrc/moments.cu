@@ -68,31 +68,45 @@ struct VecAcc {
         fma2(a01[2], f01, ny); fma2(a23[2], f23, ny);
         fma2(a01[3], f01, nz); fma2(a23[3], f23, nz);
     }
-    // entries whose row index exceeds T are not neighbours: their load is predicated off and they
-    // contribute zeros
-    UME_DEVI void gather(const float4* list, int len, int T, const float* __restrict__ feat_b) {
+    // Every warp owns a contiguous slice of the list.  If the list holds non-neighbours (row index
+    // > T) the warp first squeezes them out of its slice in place (ballot + prefix, no barrier: the
+    // write position never passes the read position), then streams the feature rows of what is
+    // left: RPW rows per warp instruction, kGU instructions in flight per lane, no predication.
+    UME_DEVI void gather(float4* list, int len, int T, const float* __restrict__ feat_b) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int per = (len + kNW - 1) / kNW;
+        const int lo = min(len, warp * per);
+        int cnt = min(len, lo + per) - lo;
+        float4* seg = list + lo;
+        if (T != 0x7fffffff) {
+            const unsigned lt = lanemask_lt();
+            int out = 0;
+            for (int i = 0; i < cnt; i += 32) {
+                const bool in = i + lane < cnt;
+                const float4 v = seg[in ? i + lane : 0];
+                const bool keep = in && __float_as_int(v.w) <= T;
+                const unsigned m = __ballot_sync(UME_FULL_MASK, keep);
+                if (keep) seg[out + __popc(m & lt)] = v;
+                out += __popc(m);
+            }
+            cnt = out;
+            __syncwarp();
+        }
         const int sub = lane / LPR, l = lane % LPR;
-        constexpr int stride = kNW * RPW;
         const float* fl = feat_b + 4 * l;
-        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        int e = warp * RPW + sub;
-        for (; e + (kGU - 1) * stride < len; e += kGU * stride) {
+        int e = sub;
+        for (; e + (kGU - 1) * RPW < cnt; e += kGU * RPW) {
             float4 nb[kGU], f[kGU];
 #pragma unroll
-            for (int u = 0; u < kGU; ++u) nb[u] = list[e + u * stride];
+            for (int u = 0; u < kGU; ++u) nb[u] = seg[e + u * RPW];
 #pragma unroll
-            for (int u = 0; u < kGU; ++u) {
-                const int j = __float_as_int(nb[u].w);
-                f[u] = (j <= T) ? ldg_f4(fl + (size_t)j * C) : zero;
-            }
+            for (int u = 0; u < kGU; ++u) f[u] = ldg_f4(fl + (size_t)__float_as_int(nb[u].w) * C);
 #pragma unroll
             for (int u = 0; u < kGU; ++u) add(nb[u], f[u]);
         }
-        for (; e < len; e += stride) {
-            const float4 nb = list[e];
-            const int j = __float_as_int(nb.w);
-            add(nb, (j <= T) ? ldg_f4(fl + (size_t)j * C) : zero);
+        for (; e < cnt; e += RPW) {
+            const float4 nb = seg[e];
+            add(nb, ldg_f4(fl + (size_t)__float_as_int(nb.w) * C));
         }
     }
     // combine the RPW row groups of the warp, then lanes [0,LPR) hold the warp's C x 4 partial
@@ -138,7 +152,7 @@ struct GenAcc {
             a[i][3] = fmaf(f, nb.z, a[i][3]);
         }
     }
-    UME_DEVI void gather(const float4* list, int len, int T, const float* __restrict__ feat_b) {
+    UME_DEVI void gather(float4* list, int len, int T, const float* __restrict__ feat_b) {
         const int warp = threadIdx.x >> 5;
         int e = warp;
         for (; e + kNW < len; e += 2 * kNW) {

@@ -14,23 +14,44 @@ namespace ume {
 static constexpr int kMaxRows = 64;       // (2*div+2)^2 <= 36 cell rows per query
 static constexpr int kHistBins = 512;
 static constexpr int kBitmapWords = 128;  // bin width <= 4096 indices  ->  N <= 512*4096 (= 2 M points per cloud)
+static constexpr int kChunkCap = 512;     // chunk-table window: runs of <= 32 candidates handed to the warps
 
 struct CollectSmem {
     int seg_start[kMaxRows];
     int seg_prefix[kMaxRows + 1];
+    int seg_chunk0[kMaxRows + 1];         // exclusive prefix of the rows' chunk counts
+    unsigned chunk[kChunkCap];            // (position in the sorted array << 5) | (candidates - 1)
     unsigned hist[kHistBins];
     unsigned bitmap[kBitmapWords];
     int warp_cnt[32];
     int count;        // hits appended so far (may exceed the list capacity)
     int sel_bin, sel_below, sel_T;
-    int nrows, total;
+    int nrows, total, nchunks;
 };
+
+// shared-memory atomic add through PTX: keeps nvcc from wrapping a one-lane atomic in its own
+// warp-aggregation sequence (vote + find-leader + shuffle, ~16 instructions)
+UME_DEVI int smem_add(int* p, int v) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;"
+                 : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    return old;
+}
+
+// One row's share of the chunk table for the window of chunk ids [w0, w0 + kChunkCap): the run
+// (start s, n candidates) is cut into pieces of 32; c0 = id of its first chunk.
+UME_DEVI void fill_chunks(CollectSmem& sm, int s, int n, int c0, int w0) {
+    const int nch = (n + 31) >> 5;
+    const int k1 = min(nch, w0 + kChunkCap - c0);
+    for (int k = max(0, w0 - c0); k < k1; ++k)
+        sm.chunk[c0 + k - w0] = ((unsigned)(s + 32 * k) << 5) | (unsigned)(min(32, n - 32 * k) - 1);
+}
 
 // ---------------------------------------------------------------- phase 0: candidate runs
 template <int NT>
 UME_DEVI void collect_rows(CollectSmem& sm, const GridHeader& h, const int* __restrict__ cs, float kx,
                            float ky, float kz, float radius) {
-    static_assert(NT >= kMaxRows, "one thread per candidate row");
+    static_assert(NT >= 2 * kMaxRows, "one thread per candidate row, the others clear the histogram");
     if (threadIdx.x < kMaxRows) {
         const float r = fabsf(radius);
         const float mx = r * 1e-4f + fabsf(kx) * 1e-6f + 1e-7f;
@@ -75,22 +96,29 @@ UME_DEVI void collect_rows(CollectSmem& sm, const GridHeader& h, const int* __re
             }
             sm.seg_start[row] = s;
         }
-        // exclusive prefix of the run lengths over the (<= 64) rows: two warps, shuffle scan
+        // inclusive prefixes of the run lengths and of the chunk counts over the (<= 64) rows: two
+        // warps, shuffle scans, the second warp fixed up after the barrier
         const int lane = threadIdx.x & 31;
-        int incl = n;
+        int incl = n, cincl = (n + 31) >> 5;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(UME_FULL_MASK, incl, o);
-            if (lane >= o) incl += v;
+            const int c = __shfl_up_sync(UME_FULL_MASK, cincl, o);
+            if (lane >= o) { incl += v; cincl += c; }
         }
-        if (threadIdx.x == 31) sm.warp_cnt[0] = incl;
-        if (threadIdx.x == 0) { sm.nrows = nrows; sm.count = 0; sm.seg_prefix[0] = 0; }
-        sm.seg_prefix[row + 1] = incl;               // second warp fixed up below
+        if (threadIdx.x == 31) { sm.warp_cnt[0] = incl; sm.warp_cnt[1] = cincl; }
+        if (threadIdx.x == 0) { sm.nrows = nrows; sm.count = 0; sm.seg_prefix[0] = 0; sm.seg_chunk0[0] = 0; }
+        __syncthreads();
+        if (threadIdx.x >= 32) { incl += sm.warp_cnt[0]; cincl += sm.warp_cnt[1]; }
+        sm.seg_prefix[row + 1] = incl;
+        sm.seg_chunk0[row + 1] = cincl;
+        if (row == kMaxRows - 1) { sm.total = incl; sm.nchunks = cincl; }   // rows >= nrows are empty
+        fill_chunks(sm, s, n, cincl - ((n + 31) >> 5), 0);
+    } else {
+        // the warps without rows clear the row-index histogram the scan fills (select_kth_index)
+        for (int i = threadIdx.x - kMaxRows; i < kHistBins; i += NT - kMaxRows) sm.hist[i] = 0;
+        __syncthreads();
     }
-    __syncthreads();
-    if (threadIdx.x >= 32 && threadIdx.x < kMaxRows) sm.seg_prefix[threadIdx.x + 1] += sm.warp_cnt[0];
-    __syncthreads();
-    if (threadIdx.x == 0) sm.total = sm.seg_prefix[sm.nrows];
     __syncthreads();
 }
 
@@ -142,70 +170,65 @@ UME_DEVI void append_hit(CollectSmem& sm, float4* list, int cap, bool hit, float
 }
 
 // ---------------------------------------------------------------- first pass: warp-granular scan + append
-// Every warp takes runs of 32 consecutive candidates that lie inside ONE cell row, so the walk over
-// the rows is warp-uniform (no per-thread search, no divergence) and one shared-memory atomic per 32
-// candidates reserves the slots of the hits.  The next run is loaded before the current one is
-// tested (two 16-byte loads in flight per lane).  Trip counts differ between warps, so nothing in
-// here may synchronise the CTA.
+// The candidates of the query are cut into chunks of <= 32 consecutive entries of one cell row
+// (chunk table, built once per query by the row threads).  Every warp takes chunks warp, warp + NW,
+// ...: two per iteration, the next two already loading while the current two are tested (four
+// 16-byte loads in flight per lane), one shared-memory atomic per iteration reserving the slots of
+// the hits of both.  Every hit is also counted in the histogram of (row index >> shift), whether or
+// not it still fits the list: level 1 of the counting select comes for free.  Trip counts differ between warps, so nothing in here may synchronise the CTA.
 template <bool kFma, int NT>
 UME_DEVI void scan_append(CollectSmem& sm, float4* list, int cap, const float4* __restrict__ sorted_b, float kx,
-                          float ky, float kz, float r2) {
+                          float ky, float kz, float r2, int nch, int shift) {
     constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nrows = sm.nrows;
-    int seg = 0, c = warp;                                // cursor: chunk c of run `seg`
-    int seg_len = sm.seg_prefix[1], seg_chunks = (seg_len + 31) >> 5;
-    auto next_run = [&](int& pos, int& cnt) -> bool {
-        while (seg < nrows && c >= seg_chunks) {
-            c -= seg_chunks;
-            ++seg;
-            if (seg < nrows) {
-                seg_len = sm.seg_prefix[seg + 1] - sm.seg_prefix[seg];
-                seg_chunks = (seg_len + 31) >> 5;
-            }
+    const unsigned lt = lanemask_lt();
+    auto fetch = [&](int c, float4& v, int& cnt) {
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+        cnt = 0;
+        if (c < nch) {                                   // warp-uniform
+            const unsigned e = sm.chunk[c];
+            cnt = (int)(e & 31u) + 1;
+            if (lane < cnt) v = __ldg(&sorted_b[(e >> 5) + lane]);
         }
-        if (seg >= nrows) return false;
-        pos = sm.seg_start[seg] + c * 32;
-        cnt = seg_len - c * 32;
-        c += NW;
-        return true;
     };
-    int pos, cnt;
-    bool have = (nrows > 0) && next_run(pos, cnt);
-    float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (have && lane < cnt) cur = __ldg(&sorted_b[pos + lane]);
-    while (have) {
-        const int cur_cnt = cnt;
-        int npos, ncnt;
-        const bool have_next = next_run(npos, ncnt);
-        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (have_next && lane < ncnt) nxt = __ldg(&sorted_b[npos + lane]);
-        const float ex = __fsub_rn(cur.x, kx), ey = __fsub_rn(cur.y, ky), ez = __fsub_rn(cur.z, kz);
-        const bool hit = (lane < cur_cnt) && (dist2_ordered<kFma>(ex, ey, ez) < r2);
-        const unsigned m = __ballot_sync(UME_FULL_MASK, hit);
-        if (m) {
+    float4 a, b;
+    int ca, cb;
+    fetch(warp, a, ca);
+    fetch(warp + NW, b, cb);
+    for (int c = warp; c < nch; c += 2 * NW) {
+        float4 na, nb;
+        int nca, ncb;
+        fetch(c + 2 * NW, na, nca);
+        fetch(c + 3 * NW, nb, ncb);
+        const float ax = __fsub_rn(a.x, kx), ay = __fsub_rn(a.y, ky), az = __fsub_rn(a.z, kz);
+        const float bx = __fsub_rn(b.x, kx), by = __fsub_rn(b.y, ky), bz = __fsub_rn(b.z, kz);
+        const bool ha = (lane < ca) && (dist2_ordered<kFma>(ax, ay, az) < r2);
+        const bool hb = (lane < cb) && (dist2_ordered<kFma>(bx, by, bz) < r2);
+        const unsigned ma = __ballot_sync(UME_FULL_MASK, ha), mb = __ballot_sync(UME_FULL_MASK, hb);
+        if (ha) atomicAdd(&sm.hist[__float_as_int(a.w) >> shift], 1u);     // level 1 of the counting select
+        if (hb) atomicAdd(&sm.hist[__float_as_int(b.w) >> shift], 1u);
+        if (ma | mb) {
+            const int na_hits = __popc(ma);
             int base = 0;
-            if (lane == 0) base = atomicAdd(&sm.count, __popc(m));
+            if (lane == 0) base = smem_add(&sm.count, na_hits + __popc(mb));
             base = __shfl_sync(UME_FULL_MASK, base, 0);
-            const int slot = base + __popc(m & lanemask_lt());
-            if (hit && slot < cap) list[slot] = make_float4(ex, ey, ez, cur.w);
+            const int sa = base + __popc(ma & lt), sb = base + na_hits + __popc(mb & lt);
+            if (ha && sa < cap) list[sa] = make_float4(ax, ay, az, a.w);
+            if (hb && sb < cap) list[sb] = make_float4(bx, by, bz, b.w);
         }
-        cur = nxt;
-        cnt = ncnt;
-        have = have_next;
+        a = na; b = nb;
+        ca = nca; cb = ncb;
     }
 }
 
 // ---------------------------------------------------------------- counting select
 // Given that more than K candidates are in radius, find T = the K-th smallest row index among
-// them.  `each(f)` must call f(row_index) once per in-radius candidate (any thread, any order).
+// them.  sm.hist already holds the histogram of (row index >> shift) over ALL in-radius candidates
+// (filled by scan_append, visible after a barrier).  `each(f)` must call f(row_index) once per
+// in-radius candidate (any thread, any order): it resolves the bin the K-th index falls in.
 template <int NT, typename Each>
 UME_DEVI int select_kth_index(CollectSmem& sm, int K, int shift, Each each) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < kHistBins; i += NT) sm.hist[i] = 0;
-    __syncthreads();
-    each([&](int idx) { atomicAdd(&sm.hist[idx >> shift], 1u); });
-    __syncthreads();
     {
         constexpr int per = kHistBins / NT;
         const int lo = tid * per;
@@ -322,11 +345,20 @@ UME_DEVI int collect_neighbors(CollectSmem& sm, float4* list, int cap, const Gri
                                float ky, float kz, float radius, int K, Flush flush) {
     const float r2 = __fmul_rn(radius, radius);
     collect_rows<NT>(sm, h, cs, kx, ky, kz, radius);
-    scan_append<kFma, NT>(sm, list, cap, sorted_b, kx, ky, kz, r2);
+    const int nchunks = sm.nchunks;
+    const int shift = max(0, 23 - __clz(N - 1));         // smallest shift with (N-1) >> shift < kHistBins
+    for (int w0 = 0;;) {
+        scan_append<kFma, NT>(sm, list, cap, sorted_b, kx, ky, kz, r2, min(kChunkCap, nchunks - w0), shift);
+        w0 += kChunkCap;
+        if (w0 >= nchunks) break;                        // the usual case: one window
+        __syncthreads();
+        if (threadIdx.x < kMaxRows)
+            fill_chunks(sm, sm.seg_start[threadIdx.x], sm.seg_prefix[threadIdx.x + 1] - sm.seg_prefix[threadIdx.x],
+                        sm.seg_chunk0[threadIdx.x], w0);
+        __syncthreads();
+    }
     __syncthreads();
     const int count = sm.count;
-    int shift = 0;
-    while (((N - 1) >> shift) >= kHistBins) ++shift;
     if (count <= cap) {
         int len = count, T = 0x7fffffff;
         if (count > K) {
