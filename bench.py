@@ -68,6 +68,7 @@ def parse():
     ap.add_argument("--workload", default="kitti_b64_n1024_c32", choices=sorted(WORKLOADS))
     ap.add_argument("--cdist-impl", type=int, default=None, help="0 = SIMT fp32, 1 = tcgen05")
     ap.add_argument("--cell-div2", type=int, default=None)
+    ap.add_argument("--cta-moments", type=int, default=None, help="1 = force the CTA-per-keypoint moment kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-pairs", type=int, default=24)
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -155,6 +156,8 @@ def run_b200(args, wl):
         ume.config["cdist_impl"] = args.cdist_impl
     if args.cell_div2 is not None:
         ume.config["cell_div2"] = bool(args.cell_div2)
+    if args.cta_moments is not None:
+        ume.config["cta_moments"] = bool(args.cta_moments)
 
     batch_np = make_workload(wl, seed0=10000 * rank)
     keys = ("src_pts", "src_feat", "src_kp", "tgt_pts", "tgt_feat", "tgt_kp")
@@ -272,13 +275,14 @@ def run_b200(args, wl):
                    "keypoints": wl["n_kp"], "channels": wl["C"], "K": K_NN, "radius": RADIUS,
                    "mean_neighbours": float(0.5 * (cnt_s.mean() + cnt_t.mean())),
                    "cdist_impl": ume.config["cdist_impl"], "cell_div2": ume.config["cell_div2"], "cuda_graph": use_graph,
+                   "moment_kernel": "cta-per-keypoint" if ume.config["cta_moments"] else "warp-per-keypoint",
                    "l2_policy": "inputs (%.1f GB per step) exceed the 126 MB L2" % (h2d / 1e9),
                    "parallelism": "pairs sharded over %d GPU(s), one all-gather of results per step" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": args.e2e_steps, "ms_per_step": e2e_ms / max(args.e2e_steps, 1)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "moments_kernel (fused gather + UME moments)", "bound": "hbm",
+        "roofline": {"kernel": "moments_%s_kernel (fused gather + UME moments)" % ("cta" if ume.config["cta_moments"] else "warp"), "bound": "hbm",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
                      "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": mom_avg_ms,

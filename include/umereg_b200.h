@@ -43,6 +43,8 @@ typedef enum ume_status {
                                       pytorch3d's CUDA kernel); default: separately rounded mul/add
                                       (pytorch3d CPU build, torch/numpy restatements)           */
 #define UME_FLAG_CELL_DIV2     2u  /* search grid with cell = radius/2 instead of radius        */
+#define UME_FLAG_CTA_MOMENTS   4u  /* ume_moments_f32: force the CTA-per-keypoint kernel (the default
+                                      for C in {16,32,64,128} is the warp-per-keypoint kernel)      */
 
 int ume_abi_version(void);
 const char* ume_last_error(void);

@@ -19,7 +19,16 @@ def ume():
     from umeregrobust_b200 import _lib
     _lib.lib()                                   # fails loudly when the CUDA library is missing
     yield u
-    u.config.update(fma_dist=False, cell_div2=False, cdist_impl=None)
+    u.config.update(fma_dist=False, cell_div2=False, cdist_impl=None, cta_moments=False)
+
+
+@pytest.fixture(params=["warp", "cta"])
+def moment_kernel(request, ume):
+    """Both gather+moment kernels: one warp per keypoint (default for C in {16,32,64,128}) and one CTA
+    per keypoint (every other channel count, or forced with config['cta_moments'])."""
+    ume.config.update(cta_moments=(request.param == "cta"))
+    yield request.param
+    ume.config.update(cta_moments=False)
 
 
 def dev(x):
@@ -89,7 +98,7 @@ def test_ball_query_edge_cases(ume):
 
 # ----------------------------------------------------------------------------- moments
 @pytest.mark.parametrize("C", [4, 8, 16, 32, 64, 128, 12, 33, 200])
-def test_moments_all_channel_counts(ume, C):
+def test_moments_all_channel_counts(ume, moment_kernel, C):
     N, n, K, radius = 4000, 48, 200, 3.0
     pts, rng = cloud(C, 2, N)
     feat = synth._normalize_rows(rng.normal(size=(2, N, C))).astype(np.float32)
@@ -112,7 +121,7 @@ def test_moments_all_channel_counts(ume, C):
     (30000, 16, 100000, 6.0),   # K > N: every hit used, chunked
     (2000, 2000, 64, 1.5),      # every point a keypoint
 ])
-def test_moments_overflow_and_large_k(ume, N, n, K, radius):
+def test_moments_overflow_and_large_k(ume, moment_kernel, N, n, K, radius):
     pts, rng = cloud(N + K, 1, N, spread=18.0)
     feat = synth._normalize_rows(rng.normal(size=(1, N, 32))).astype(np.float32)
     kp = pts[:, rng.choice(N, n, replace=False)].copy()
@@ -123,7 +132,28 @@ def test_moments_overflow_and_large_k(ume, N, n, K, radius):
     assert moment_err(host(F), F64, kappa) < 2e-6
 
 
-def test_moments_fma_mode_changes_only_boundary_points(ume):
+@pytest.mark.parametrize("order", ["x", "morton", "random"])
+@pytest.mark.parametrize("N,K", [(70000, 750), (300000, 40), (20000, 1), (20000, 3000)])
+def test_moments_row_order_structures(ume, moment_kernel, order, N, K):
+    """The K-th smallest row index is found through histograms of the row indices: spatially
+    coherent row orders (an unpermuted sweep) pile many in-radius rows into one histogram bin and
+    force the refinement levels; a random permutation spreads them."""
+    pts, rng = cloud(N + K, 1, N, spread=25.0)
+    if order == "x":
+        pts = pts[:, np.argsort(pts[0, :, 0], kind="stable")]
+    elif order == "morton":
+        cell = np.floor((pts[0] - pts[0].min(0)) / 2.0).astype(np.int64)
+        pts = pts[:, np.lexsort((pts[0, :, 2], cell[:, 0], cell[:, 1]))]
+    feat = synth._normalize_rows(rng.normal(size=(1, N, 32))).astype(np.float32)
+    kp = pts[:, rng.choice(N, 40, replace=False)].copy()
+    F64, idx = orc.ume_moments(pts, kp, feat, K, 5.0, dtype=np.float64, return_idx=True)
+    kappa = orc.normaliser_condition(feat, idx)
+    F, cnt = ume.ume_moments(dev(pts), dev(kp), dev(feat), K, 5.0, return_count=True)
+    assert np.array_equal(host(cnt), (idx >= 0).sum(-1))
+    assert moment_err(host(F), F64, kappa) < 2e-6
+
+
+def test_moments_fma_mode_changes_only_boundary_points(ume, moment_kernel):
     pts, rng = cloud(77, 1, 20000)
     feat = synth._normalize_rows(rng.normal(size=(1, 20000, 8))).astype(np.float32)
     kp = pts[:, :256].copy()

@@ -19,6 +19,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 UME_FLAG_FMA_DIST = 1
 UME_FLAG_CELL_DIV2 = 2
+UME_FLAG_CTA_MOMENTS = 4
 
 _lock = threading.Lock()
 _lib = None

@@ -21,13 +21,14 @@ _KNN = collections.namedtuple("_KNN", ["dists", "idx", "knn"])
 #   cell_div2: search grid with cell = radius / 2
 #   cdist_impl: 0 = fp32 SIMT distance kernel, 1 = tcgen05 tensor-core kernel
 #               (C = 32 / 64 only), None = tensor cores whenever the channel count allows
-config = {"fma_dist": False, "cell_div2": False, "cdist_impl": None}
+config = {"fma_dist": False, "cell_div2": False, "cdist_impl": None, "cta_moments": False}
 
 _workspaces = {}
 
 
 def _flags():
-    return (_lib.UME_FLAG_FMA_DIST if config["fma_dist"] else 0) | (_lib.UME_FLAG_CELL_DIV2 if config["cell_div2"] else 0)
+    return ((_lib.UME_FLAG_FMA_DIST if config["fma_dist"] else 0) | (_lib.UME_FLAG_CELL_DIV2 if config["cell_div2"] else 0)
+            | (_lib.UME_FLAG_CTA_MOMENTS if config["cta_moments"] else 0))
 
 
 def _stream():

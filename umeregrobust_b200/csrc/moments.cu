@@ -8,6 +8,7 @@
 // reference does and written as one 16-byte row per channel.  The (B,n,K,C) gather tensor the
 // reference materialises (evaluate.py:54-55) never exists.
 #include "neighbors.cuh"
+#include "moments_warp.cuh"
 
 namespace ume {
 
@@ -283,6 +284,22 @@ extern "C" int ume_moments_f32(const float* pts, const float* kpts, const float*
     p.kpts = kpts; p.feat = feat; p.F = F; p.Fc = Fc; p.count = count;
     p.n = n; p.C = C; p.K = K; p.cap = moments_cap(C, K); p.radius = radius;
     const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
+    const bool aligned = reinterpret_cast<uintptr_t>(feat) % 16 == 0;
+    if (!(flags & UME_FLAG_CTA_MOMENTS) && aligned && (C == 16 || C == 32 || C == 64 || C == 128)) {
+        // one warp per keypoint (moments_warp.cuh): the default for the channel counts it is built for
+        warpk::Params wp;
+        wp.grid = p.grid; wp.kpts = kpts; wp.feat = feat; wp.F = F; wp.Fc = Fc; wp.count = count;
+        wp.n = n; wp.K = K; wp.total = (long long)B * n; wp.radius = radius;
+        wp.next = w.take<unsigned long long>(1);
+        UME_REQUIRE(w.ok(), UME_ERR_WORKSPACE, "ume_moments_f32: workspace too small for the work counter");
+        ProfScope prof(UME_PROF_MOMENTS, stream);
+        switch (C) {
+            case 16: return warpk::launch<4>(wp, fma, stream);
+            case 32: return warpk::launch<8>(wp, fma, stream);
+            case 64: return warpk::launch<16>(wp, fma, stream);
+            default: return warpk::launch<32>(wp, fma, stream);
+        }
+    }
     const bool vec = (C % 4 == 0) && ((C & (C - 1)) == 0) && C >= 4 && C <= 128 &&
                      (reinterpret_cast<uintptr_t>(feat) % 16 == 0);
     if (vec) {

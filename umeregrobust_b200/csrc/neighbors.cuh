@@ -48,52 +48,74 @@ UME_DEVI void fill_chunks(CollectSmem& sm, int s, int n, int c0, int w0) {
 }
 
 // ---------------------------------------------------------------- phase 0: candidate runs
+// The cells a query's ball can touch, as <= kMaxRows runs of the cell-sorted array: one run per
+// (y,z) cell row, its x range trimmed to the chord of the (slightly inflated) ball.
+struct RowSetup {
+    int cx0, cx1, cy0, cz0, nyr, nrows;
+    float rr2, mx;
+};
+
+UME_DEVI RowSetup row_setup(const GridHeader& h, float kx, float ky, float kz, float radius) {
+    RowSetup rs;
+    const float r = fabsf(radius);
+    const float mx = r * 1e-4f + fabsf(kx) * 1e-6f + 1e-7f;
+    const float my = r * 1e-4f + fabsf(ky) * 1e-6f + 1e-7f;
+    const float mz = r * 1e-4f + fabsf(kz) * 1e-6f + 1e-7f;
+    rs.cx0 = cell_coord(kx - r - mx, h.ox, h.inv_s, h.nx);
+    rs.cx1 = cell_coord(kx + r + mx, h.ox, h.inv_s, h.nx);
+    rs.cy0 = cell_coord(ky - r - my, h.oy, h.inv_s, h.ny);
+    const int cy1 = cell_coord(ky + r + my, h.oy, h.inv_s, h.ny);
+    rs.cz0 = cell_coord(kz - r - mz, h.oz, h.inv_s, h.nz);
+    const int cz1 = cell_coord(kz + r + mz, h.oz, h.inv_s, h.nz);
+    rs.nyr = cy1 - rs.cy0 + 1;
+    rs.nrows = min(rs.nyr * (cz1 - rs.cz0 + 1), kMaxRows);   // the cap cannot bind: cell >= radius/2 (grid_params_kernel)
+    const float rr = (r + 4.f * (mx + my + mz));
+    rs.rr2 = rr * rr;
+    rs.mx = mx;
+    return rs;
+}
+
+// run of candidate row `row` (< rs.nrows): start `s` in the sorted array and length `n`
+UME_DEVI void row_run(const RowSetup& rs, const GridHeader& h, const int* __restrict__ cs, float kx, float ky,
+                      float kz, int row, int& s, int& n) {
+    s = 0;
+    n = 0;
+    const int iy = rs.cy0 + row % rs.nyr, iz = rs.cz0 + row / rs.nyr;
+    // prune rows / trim the x range by the distance from the query to the cell slab; the
+    // outermost cells also hold clamped coordinates, so they are treated as unbounded
+    float dy = 0.f, dz = 0.f;
+    {
+        float lo = h.oy + (float)iy * h.s, hi = lo + h.s;
+        if (iy > 0 && ky < lo) dy = lo - ky;
+        if (iy < h.ny - 1 && ky > hi) dy = ky - hi;
+        lo = h.oz + (float)iz * h.s; hi = lo + h.s;
+        if (iz > 0 && kz < lo) dz = lo - kz;
+        if (iz < h.nz - 1 && kz > hi) dz = kz - hi;
+    }
+    const float rem2 = rs.rr2 - dy * dy - dz * dz;
+    if (rem2 > 0.f) {
+        const float half = sqrtf(rem2) * 1.0001f + rs.mx;
+        const int tx0 = max(rs.cx0, cell_coord(kx - half, h.ox, h.inv_s, h.nx));
+        const int tx1 = min(rs.cx1, cell_coord(kx + half, h.ox, h.inv_s, h.nx));
+        if (tx1 >= tx0) {
+            const int base = (iz * h.ny + iy) * h.nx;
+            s = cs[base + tx0];
+            n = cs[base + tx1 + 1] - s;
+        }
+    }
+}
+
 template <int NT>
 UME_DEVI void collect_rows(CollectSmem& sm, const GridHeader& h, const int* __restrict__ cs, float kx,
                            float ky, float kz, float radius) {
     static_assert(NT >= 2 * kMaxRows, "one thread per candidate row, the others clear the histogram");
     if (threadIdx.x < kMaxRows) {
-        const float r = fabsf(radius);
-        const float mx = r * 1e-4f + fabsf(kx) * 1e-6f + 1e-7f;
-        const float my = r * 1e-4f + fabsf(ky) * 1e-6f + 1e-7f;
-        const float mz = r * 1e-4f + fabsf(kz) * 1e-6f + 1e-7f;
-        const int cx0 = cell_coord(kx - r - mx, h.ox, h.inv_s, h.nx);
-        const int cx1 = cell_coord(kx + r + mx, h.ox, h.inv_s, h.nx);
-        const int cy0 = cell_coord(ky - r - my, h.oy, h.inv_s, h.ny);
-        const int cy1 = cell_coord(ky + r + my, h.oy, h.inv_s, h.ny);
-        const int cz0 = cell_coord(kz - r - mz, h.oz, h.inv_s, h.nz);
-        const int cz1 = cell_coord(kz + r + mz, h.oz, h.inv_s, h.nz);
-        const int nyr = cy1 - cy0 + 1, nzr = cz1 - cz0 + 1;
-        int nrows = nyr * nzr;
-        if (nrows > kMaxRows) nrows = kMaxRows;     // cannot happen: cell >= radius/2 (see grid_params_kernel)
-        const float rr = (r + 4.f * (mx + my + mz));
-        const float rr2 = rr * rr;
+        const RowSetup rs = row_setup(h, kx, ky, kz, radius);
+        const int nrows = rs.nrows;
         const int row = threadIdx.x;
         int s = 0, n = 0;
         if (row < nrows) {
-            const int iy = cy0 + row % nyr, iz = cz0 + row / nyr;
-            // prune rows / trim the x range by the distance from the query to the cell slab; the
-            // outermost cells also hold clamped coordinates, so they are treated as unbounded
-            float dy = 0.f, dz = 0.f;
-            {
-                float lo = h.oy + (float)iy * h.s, hi = lo + h.s;
-                if (iy > 0 && ky < lo) dy = lo - ky;
-                if (iy < h.ny - 1 && ky > hi) dy = ky - hi;
-                lo = h.oz + (float)iz * h.s; hi = lo + h.s;
-                if (iz > 0 && kz < lo) dz = lo - kz;
-                if (iz < h.nz - 1 && kz > hi) dz = kz - hi;
-            }
-            const float rem2 = rr2 - dy * dy - dz * dz;
-            if (rem2 > 0.f) {
-                const float half = sqrtf(rem2) * 1.0001f + mx;
-                const int tx0 = max(cx0, cell_coord(kx - half, h.ox, h.inv_s, h.nx));
-                const int tx1 = min(cx1, cell_coord(kx + half, h.ox, h.inv_s, h.nx));
-                if (tx1 >= tx0) {
-                    const int base = (iz * h.ny + iy) * h.nx;
-                    s = cs[base + tx0];
-                    n = cs[base + tx1 + 1] - s;
-                }
-            }
+            row_run(rs, h, cs, kx, ky, kz, row, s, n);
             sm.seg_start[row] = s;
         }
         // inclusive prefixes of the run lengths and of the chunk counts over the (<= 64) rows: two
