@@ -33,6 +33,12 @@ namespace warpk {
 #ifndef UME_WARPK_PERSISTENT
 #define UME_WARPK_PERSISTENT 0     // 1: warps pull keypoints from a global counter; 0: one keypoint per warp
 #endif
+#ifndef UME_WARPK_D1
+#define UME_WARPK_D1 4             // candidate chunks in flight per warp in the histogram passes
+#endif
+#ifndef UME_WARPK_D2
+#define UME_WARPK_D2 2             // ... in the gather pass (next to the feature-row loads)
+#endif
 #ifndef UME_WARPK_UNROLL
 #define UME_WARPK_UNROLL 4         // feature-row loads in flight per lane
 #endif
@@ -41,12 +47,13 @@ constexpr int kChunks = 128;       // chunk-table window per warp
 constexpr int kBins = 256;
 constexpr int kRing = 128;
 constexpr int kMaybe = 32;
+constexpr int kPad = 4;          // chunk-table entries past the end that prefetches may read
 
 struct WarpSmem {
     int seg_start[kMaxRows];
     int seg_n[kMaxRows];
     int seg_c0[kMaxRows];
-    unsigned chunk[kChunks + 4];   // (position in the sorted array << 5) | (candidates - 1); 3 pad entries
+    unsigned chunk[kChunks + 2 * kPad];   // (position in the sorted array << 5) | (candidates - 1), padded
     unsigned hist[kBins];
     float4 ring[kRing];
     float4 maybe[kMaybe];
@@ -65,6 +72,28 @@ struct Params {
     float radius;
 };
 
+// ---- shared memory through explicit 32-bit addresses: one register holds the warp's base, every
+// access is a single LDS/STS/ATOMS (nvcc otherwise re-derives the shared window base per access)
+UME_DEVI unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+UME_DEVI unsigned lds_u32(unsigned a) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+UME_DEVI float4 lds_f4(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+UME_DEVI void sts_u32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+UME_DEVI void sts_f4_if(bool p, unsigned a, float x, float y, float z, float w) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.v4.f32 [%1], {%2, %3, %4, %5}; }"
+                 ::"r"((unsigned)p), "r"(a), "f"(x), "f"(y), "f"(z), "f"(w));
+}
+UME_DEVI void inc_if(bool p, unsigned a) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q red.shared.add.u32 [%1], 1; }" ::"r"((unsigned)p), "r"(a));
+}
+
 // chunk-table window [w0, w0 + kChunks) from the per-row runs (lanes own rows lane, lane + 32)
 UME_DEVI void fill_window(WarpSmem& sm, int nrows, int nchunks, int w0) {
     const int lane = threadIdx.x & 31;
@@ -75,20 +104,21 @@ UME_DEVI void fill_window(WarpSmem& sm, int nrows, int nchunks, int w0) {
         for (int k = max(0, w0 - c0); k < k1; ++k)
             sm.chunk[c0 + k - w0] = ((unsigned)(s + 32 * k) << 5) | (unsigned)(min(32, n - 32 * k) - 1);
     }
-    if (lane < 3) sm.chunk[min(kChunks, nchunks - w0) + lane] = 0u;   // prefetches past the end read entry 0
+    if (lane < kPad) sm.chunk[min(kChunks, nchunks - w0) + lane] = 0u;   // prefetches past the end read entry 0
     __syncwarp();
 }
 
 // Walk every candidate of the query: visit(hit, ex, ey, ez, row) is called by the converged warp once
-// per chunk (lane = candidate; e = point - query).  Two chunks are in flight: the loop is unrolled
-// by two so that the buffers rotate without register moves, and the table is padded so that the
-// prefetch needs no bounds check.
-template <bool kFma, typename Visit>
+// per chunk (lane = candidate; e = point - query).  D chunks are in flight: the loop is unrolled by
+// D so that the buffers rotate without register moves, the table is padded so that the prefetch
+// needs no bounds check, and lanes past the end of a short chunk re-read its last entry so that
+// the load needs no predicate.
+template <bool kFma, int D, typename Visit>
 UME_DEVI void scan(WarpSmem& sm, int nrows, int nchunks, int& loaded_w0, const float4* __restrict__ sorted_b,
                    float kx, float ky, float kz, float r2, Visit visit) {
-    const unsigned lane = threadIdx.x & 31;
-    const float4* base = sorted_b + lane;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    static_assert(D <= kPad, "table padding");
+    const int lane = threadIdx.x & 31;
+    const unsigned chunk_a = smem_u32(sm.chunk);
     for (int w0 = 0; w0 < nchunks; w0 += kChunks) {
         if (loaded_w0 != w0) {
             __syncwarp();
@@ -96,24 +126,24 @@ UME_DEVI void scan(WarpSmem& sm, int nrows, int nchunks, int& loaded_w0, const f
             loaded_w0 = w0;
         }
         const int nch = min(kChunks, nchunks - w0);
-        auto fetch = [&](int c, float4& v, unsigned& e) {
-            e = sm.chunk[c];
-            if (lane <= (e & 31u)) v = __ldg(base + (e >> 5));
+        float4 buf[D];
+        int last[D];                                     // candidates - 1 of the chunk in buf[i]
+        auto fetch = [&](int c, int i) {
+            const unsigned e = lds_u32(chunk_a + 4u * (unsigned)c);
+            last[i] = (int)(e & 31u);
+            buf[i] = __ldg(sorted_b + ((e >> 5) + (unsigned)min(lane, last[i])));
         };
-        auto test = [&](const float4& v, unsigned e) {
-            const float ex = __fsub_rn(v.x, kx), ey = __fsub_rn(v.y, ky), ez = __fsub_rn(v.z, kz);
-            const bool hit = (lane <= (e & 31u)) && (dist2_ordered<kFma>(ex, ey, ez) < r2);
-            visit(hit, ex, ey, ez, __float_as_int(v.w));
-        };
-        unsigned ea, eb;
-        fetch(0, a, ea);
-        fetch(1, b, eb);
-        for (int c = 0; c < nch; c += 2) {
-            test(a, ea);
-            fetch(c + 2, a, ea);
-            if (c + 1 >= nch) break;
-            test(b, eb);
-            fetch(c + 3, b, eb);
+#pragma unroll
+        for (int i = 0; i < D; ++i) fetch(i, i);
+        for (int c = 0; c < nch; c += D) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                if (i > 0 && c + i >= nch) break;            // warp-uniform
+                const float ex = __fsub_rn(buf[i].x, kx), ey = __fsub_rn(buf[i].y, ky), ez = __fsub_rn(buf[i].z, kz);
+                const bool hit = (dist2_ordered<kFma>(ex, ey, ez) < r2) & (lane <= last[i]);
+                visit(hit, ex, ey, ez, __float_as_int(buf[i].w));
+                fetch(c + i + D, i);
+            }
         }
     }
 }
@@ -184,11 +214,12 @@ __global__ void __launch_bounds__(32 * kWarps, UME_WARPK_MINB) moments_warp_kern
     // ---- pass 1: hits and the level-0 histogram of their row indices
     int shift = max(0, 24 - __clz(N - 1));        // smallest shift with (N-1) >> shift < kBins
     int my_hits = 0;
-    scan<kFma>(sm, nrows, nchunks, loaded_w0, sorted_b, kx, ky, kz, r2,
-               [&](bool hit, float, float, float, int row) {
-                   my_hits += hit ? 1 : 0;
-                   if (hit) atomicAdd(&sm.hist[row >> shift], 1u);
-               });
+    const unsigned hist_a = smem_u32(sm.hist);
+    scan<kFma, UME_WARPK_D1>(sm, nrows, nchunks, loaded_w0, sorted_b, kx, ky, kz, r2,
+                  [&](bool hit, float, float, float, int row) {
+                      my_hits += hit ? 1 : 0;
+                      inc_if(hit, hist_a + 4u * (unsigned)(row >> shift));
+                  });
     const int hits = __reduce_add_sync(UME_FULL_MASK, my_hits);
     __syncwarp();
 
@@ -239,10 +270,11 @@ __global__ void __launch_bounds__(32 * kWarps, UME_WARPK_MINB) moments_warp_kern
 #pragma unroll
             for (int i = lane; i < kBins; i += 32) sm.hist[i] = 0;
             __syncwarp();
-            scan<kFma>(sm, nrows, nchunks, loaded_w0, sorted_b, kx, ky, kz, r2,
-                       [&](bool hit, float, float, float, int row) {
-                           if (hit && row >= lo && row < hi) atomicAdd(&sm.hist[(row - lo) >> shift], 1u);
-                       });
+            scan<kFma, UME_WARPK_D1>(sm, nrows, nchunks, loaded_w0, sorted_b, kx, ky, kz, r2,
+                          [&](bool hit, float, float, float, int row) {
+                              const bool in = hit & (row >= lo) & (row < hi);
+                              inc_if(in, hist_a + 4u * (unsigned)((in ? row - lo : 0) >> shift));
+                          });
             __syncwarp();
         }
     }
@@ -262,47 +294,50 @@ __global__ void __launch_bounds__(32 * kWarps, UME_WARPK_MINB) moments_warp_kern
         a01[3] = __ffma2_rn(f01, nz, a01[3]); a23[3] = __ffma2_rn(f23, nz, a23[3]);
     };
     int wpos = 0, rpos = 0;                        // ring cursors (warp-uniform, free running)
+    const unsigned ring_a = smem_u32(sm.ring), maybe_a = smem_u32(sm.maybe);
+    const unsigned ring_sub = ring_a + 16u * (unsigned)sub;
     auto consume = [&]() {
         while (wpos - rpos >= RPW * U) {
             // a batch never wraps: RPW * U divides kRing.  Row indices first, all U feature loads in
             // flight, then the offsets are re-read from the ring as the rows arrive (registers)
-            const float4* rb = sm.ring + ((rpos & (kRing - 1)) + sub);
+            const unsigned ra = ring_sub + 16u * (unsigned)(rpos & (kRing - 1));
             float4 f[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) f[u] = ldg_f4(fl + (size_t)__float_as_int(rb[u * RPW].w) * C);
+            for (int u = 0; u < U; ++u) f[u] = ldg_f4(fl + (size_t)lds_u32(ra + 16u * (u * RPW) + 12u) * C);
 #pragma unroll
-            for (int u = 0; u < U; ++u) accumulate(rb[u * RPW], f[u]);
+            for (int u = 0; u < U; ++u) accumulate(lds_f4(ra + 16u * (u * RPW)), f[u]);
             rpos += RPW * U;
         }
     };
     auto push = [&](bool take, float ex, float ey, float ez, int row) {
         const unsigned m = __ballot_sync(UME_FULL_MASK, take);
         if (m) {
-            if (take) sm.ring[(wpos + __popc(m & lt)) & (kRing - 1)] = make_float4(ex, ey, ez, __int_as_float(row));
+            sts_f4_if(take, ring_a + 16u * (unsigned)((wpos + __popc(m & lt)) & (kRing - 1)), ex, ey, ez, __int_as_float(row));
             wpos += __popc(m);
             __syncwarp();
             consume();
         }
     };
     int n_maybe = 0;
-    scan<kFma>(sm, nrows, nchunks, loaded_w0, sorted_b, kx, ky, kz, r2,
-               [&](bool hit, float ex, float ey, float ez, int row) {
-                   const bool take = hit && row < T_lo;
-                   if (saturated) {
-                       const unsigned mm = __ballot_sync(UME_FULL_MASK, hit && !take && row < T_hi);
-                       if (mm) {                   // at most kMaybe of these per query, or exactly one (shift == 0)
-                           const int at = n_maybe + __popc(mm & lt);
-                           if (((mm >> lane) & 1u) && at < kMaybe) sm.maybe[at] = make_float4(ex, ey, ez, __int_as_float(row));
-                           n_maybe += __popc(mm);
-                       }
-                   }
-                   push(take, ex, ey, ez, row);
-               });
+    scan<kFma, UME_WARPK_D2>(sm, nrows, nchunks, loaded_w0, sorted_b, kx, ky, kz, r2,
+                  [&](bool hit, float ex, float ey, float ez, int row) {
+                      const bool take = hit & (row < T_lo);
+                      if (saturated) {
+                          const bool maybe = hit & (row >= T_lo) & (row < T_hi);
+                          const unsigned mm = __ballot_sync(UME_FULL_MASK, maybe);
+                          if (mm) {                // at most kMaybe of these per query, or exactly one (shift == 0)
+                              const int at = n_maybe + __popc(mm & lt);
+                              sts_f4_if(maybe & (at < kMaybe), maybe_a + 16u * (unsigned)min(at, kMaybe - 1), ex, ey, ez, __int_as_float(row));
+                              n_maybe += __popc(mm);
+                          }
+                      }
+                      push(take, ex, ey, ez, row);
+                  });
     __syncwarp();
     if (n_maybe > 0) {
         // the `need` smallest row indices of the crossing bin
         float4 mine = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
-        if (lane < n_maybe) mine = sm.maybe[lane];
+        if (lane < n_maybe) mine = lds_f4(maybe_a + 16u * (unsigned)lane);
         const int my_row = __float_as_int(mine.w);
         int rank = 0;
         for (int j = 0; j < n_maybe; ++j) rank += (__shfl_sync(UME_FULL_MASK, my_row, j) < my_row) ? 1 : 0;
@@ -312,7 +347,7 @@ __global__ void __launch_bounds__(32 * kWarps, UME_WARPK_MINB) moments_warp_kern
     for (; rpos < wpos; rpos += RPW) {
         const int e = rpos + sub;
         if (e < wpos) {
-            const float4 nb = sm.ring[e & (kRing - 1)];
+            const float4 nb = lds_f4(ring_a + 16u * (unsigned)(e & (kRing - 1)));
             accumulate(nb, ldg_f4(fl + (size_t)__float_as_int(nb.w) * C));
         }
     }
