@@ -163,6 +163,18 @@ int ume_corr_scores_f32(const float* src_pts, const float* tgt_pts, const float*
                         const float* T, int Ns, int Nt, int C, int n_hyp, int K, float sigma, unsigned flags,
                         float* score, int64_t* best, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- voxel de-duplication
+ * Replaces MinkowskiEngine `ME.utils.sparse_quantize(coordinates, return_index=True, quantization_size=q)`
+ * as called at evaluate.py:261-264: voxel = floor(p / q) (fp32 division); the FIRST row of every
+ * occupied voxel survives, survivors keep their row order.
+ *   pts (N,3) -> index (N) int64: the first *count entries are the surviving rows, ascending;
+ *   coords (N,3) int32: their voxel coordinates (may be NULL); count (1) int32 on the device:
+ *   number of survivors, or -1 when a coordinate was NaN or outside [-2^20, 2^20) voxels.
+ * The caller reads `count` back to size its result (the reference call is a sync point too). */
+size_t ume_voxel_unique_workspace_bytes(int N);
+int ume_voxel_unique_f32(const float* pts, int N, float voxel, int64_t* index, int32_t* coords, int32_t* count,
+                         void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- stage profiler
  * When enabled, every stage brackets its kernel launches with CUDA events on the launching
  * stream; ume_profile_read() synchronises those events and returns the accumulated device time

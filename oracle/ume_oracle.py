@@ -249,6 +249,20 @@ def feature_corr_hypothesis_test(src_pc, tgt_pc, src_feat, tgt_feat, T_kp, sigma
     return T_kp[int(np.argmax(scores))], scores                                            # :663-681
 
 
+# ----------------------------------------------------------------------------- voxel de-duplication
+def sparse_quantize(coords, quantization_size):
+    """MinkowskiEngine 0.5.4 `ME.utils.sparse_quantize(coordinates, return_index=True,
+    quantization_size=q)` (un-vendored dependency, requirements.txt; called at evaluate.py:261-264
+    and kitti_dataset.py:416): discrete = floor(coordinates / q) in the input's float32 arithmetic,
+    then the rows of the first occurrence of every distinct voxel.  ME's CPU coordinate map inserts
+    rows in order, so the returned index list is ascending.  Returns (unique (M,3) int32, index (M,) int64)."""
+    c = np.asarray(coords, dtype=np.float32)
+    disc = np.floor(c / np.float32(quantization_size)).astype(np.int32)
+    _, first = np.unique(disc, axis=0, return_index=True)
+    first = np.sort(first).astype(np.int64)
+    return disc[first], first
+
+
 # ----------------------------------------------------------------------------- whole hot path
 def register_pair_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K, radius,
                              dtype=np.float32, fma=False):

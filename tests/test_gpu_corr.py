@@ -123,3 +123,64 @@ def test_weighted_match_subsample_distribution(ume):
     assert np.abs(freq - ref).max() < 0.05
     one = ume.weighted_match_subsample(dev(d), tau, 100)
     assert one.shape == (64,) and sorted(host(one).tolist()) == list(range(64))   # k > n: everything
+
+
+@pytest.mark.parametrize("N,q", [(1, 0.3), (5000, 0.3), (200000, 0.3), (130000, 2.0), (4097, 0.05)])
+def test_sparse_quantize_bit_exact(ume, N, q):
+    # evaluate.py:261-264: same surviving rows, same order, same integer voxels as the ME restatement
+    rng = np.random.default_rng(N)
+    pts = np.concatenate([synth.disc_cloud(rng, N - N // 4), synth.disc_cloud(rng, N)[: N // 4] * 0.01], 0)[:N].astype(np.float32)
+    pts = pts[rng.permutation(len(pts))]
+    vox, idx = ume.sparse_quantize(dev(pts), return_index=True, quantization_size=q)
+    rvox, ridx = orc.sparse_quantize(pts, q)
+    assert np.array_equal(host(idx), ridx)
+    assert np.array_equal(host(vox), rvox)
+    only = ume.sparse_quantize(dev(pts), quantization_size=q)
+    assert np.array_equal(host(only), rvox)
+
+
+def test_sparse_quantize_rejects_out_of_range_and_empty(ume):
+    with pytest.raises(ValueError):
+        ume.sparse_quantize(dev(np.array([[0, 0, 0], [1e9, 0, 0]], np.float32)), return_index=True, quantization_size=0.3)
+    with pytest.raises(ValueError):
+        ume.sparse_quantize(dev(np.array([[0, np.nan, 0]], np.float32)), return_index=True, quantization_size=0.3)
+    vox, idx = ume.sparse_quantize(torch.empty((0, 3), device="cuda"), return_index=True, quantization_size=0.3)
+    assert vox.shape == (0, 3) and idx.shape == (0,)
+
+
+def test_select_hypothesis_pipeline(ume):
+    # evaluate.py:259-296 on the device: raw clouds -> voxel de-duplication -> nearest-row feature
+    # transfer -> down-sampling (draw passed in as data) -> correlator pick; against the same steps
+    # done with the oracle's pieces
+    p = synth.make_pair(5, N=20000, C=32, n_kp=256, model=synth.NUSCENES)
+    rng = np.random.default_rng(1)
+    raw_s = np.concatenate([p["src_pts"], p["src_pts"][:7000] + rng.normal(scale=0.02, size=(7000, 3))], 0).astype(np.float32)
+    raw_t = np.concatenate([p["tgt_pts"], p["tgt_pts"][:5000] + rng.normal(scale=0.02, size=(5000, 3))], 0).astype(np.float32)
+    d = {k: dev(v[None]) for k, v in p.items() if k.endswith(("pts", "feat", "kp"))}
+    out = ume.register_hypotheses(d["src_pts"], d["src_feat"], d["src_kp"], d["tgt_pts"], d["tgt_feat"], d["tgt_kp"], 750, 5.0)
+    hyp = out["T"][0].contiguous()
+    _, ks = orc.sparse_quantize(raw_s, 0.3)
+    _, kt = orc.sparse_quantize(raw_t, 0.3)
+    rs, rt = rng.permutation(len(ks))[:4000], rng.permutation(len(kt))[:4000]
+    T, best, score = ume.select_hypothesis(dev(raw_s), dev(raw_t), d["src_pts"], d["tgt_pts"], d["src_feat"], d["tgt_feat"],
+                                           hyp, corr_sigma=1.5, pc_corr_max_size=4000, src_rows=dev(rs), tgt_rows=dev(rt))
+    # reference order of operations with the oracle's pieces
+    sp, tp = raw_s[ks], raw_t[kt]
+    sf = p["src_feat"][p3d.knn_points_c(sp[None], p["src_pts"][None], 1).idx[0, :, 0]]
+    tf = p["tgt_feat"][p3d.knn_points_c(tp[None], p["tgt_pts"][None], 1).idx[0, :, 0]]
+    sc = host(score)
+    top = np.argsort(-sc)[:5]
+    ref_sc = orc.feature_corr_hypothesis_test(sp[rs][None], tp[rt][None], sf[rs][None], tf[rt][None], host(hyp)[top],
+                                              sigma=1.5, corr_num_nn=20)[1]
+    assert np.abs(ref_sc - sc[top]).max() < 2e-4 * np.abs(sc[top]).max()
+    assert int(best) == int(top[0]) and np.array_equal(host(T), host(hyp)[int(best)])
+    # sanity against the ground truth (a reduced setting: 256 keypoints, 4000 correlation points —
+    # looser than the full-size thresholds of test_end_to_end_pair_registration_recovers_ground_truth)
+    ang = np.rad2deg(orc.rotation_angle_rad(host(T)[:3, :3].astype(np.float64), p["gt"][:3, :3].astype(np.float64)))
+    terr = float(np.linalg.norm(host(T)[:3, 3] - p["gt"][:3, 3]))
+    assert ang < 5.0 and terr < 2.0, (ang, terr)
+    # default draw (device RNG) still lands on a good hypothesis
+    T2, _, _ = ume.select_hypothesis(dev(raw_s), dev(raw_t), d["src_pts"], d["tgt_pts"], d["src_feat"], d["tgt_feat"],
+                                     hyp, corr_sigma=1.5, pc_corr_max_size=4000, generator=torch.Generator(device="cuda").manual_seed(0))
+    ang2 = np.rad2deg(orc.rotation_angle_rad(host(T2)[:3, :3].astype(np.float64), p["gt"][:3, :3].astype(np.float64)))
+    assert ang2 < 5.0, ang2

@@ -171,3 +171,17 @@ def test_exact_recovery_from_local_ume():
     ang = orc.rotation_angle_rad(out["T"][0, :, :3, :3], p["gt"][:3, :3].astype(np.float64))
     assert ang.max() < 1e-4
     assert np.abs(out["T"][0, :, :3, 3] - p["gt"][:3, 3]).max() < 5e-3
+
+
+def test_sparse_quantize_known_answer():
+    # rows 0 and 2 share voxel (0,0,0), rows 1 and 4 share (-1,0,3); first occurrences survive in row order
+    c = np.array([[0.1, 0.2, 0.29], [-0.1, 0.0, 0.95], [0.29, 0.0, 0.0], [0.3, 0.0, 0.0], [-0.29, 0.1, 1.1]], np.float32)
+    vox, idx = orc.sparse_quantize(c, 0.3)
+    assert idx.tolist() == [0, 1, 3]
+    assert vox.tolist() == [[0, 0, 0], [-1, 0, 3], [1, 0, 0]]
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-50, 50, (20000, 3)).astype(np.float32)
+    vox, idx = orc.sparse_quantize(pts, 1.0)
+    assert np.all(np.diff(idx) > 0) and len(np.unique(vox, axis=0)) == len(vox)
+    # idempotent: the survivors are all distinct voxels
+    assert len(orc.sparse_quantize(pts[idx], 1.0)[1]) == len(idx)

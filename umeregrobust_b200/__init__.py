@@ -10,7 +10,8 @@ from .api import (ball_query, knn_points, knn_gather, knn1_transfer, ume_moments
                   create_local_ume_matrix, ume_descriptors, descriptor_cdist, ume_cdist, rigid_solve,
                   batch_estimate_transform_ume_old, relative_rotation_error, ball_query_gather, ume_kp_layer,
                   register_hypotheses, feature_spatial_var, cauchy_kernel, correlation_scores,
-                  pc_corr_cost_pytorch3d, weighted_features, FeatureCorrelator, weighted_match_subsample, config)
+                  pc_corr_cost_pytorch3d, weighted_features, FeatureCorrelator, weighted_match_subsample, sparse_quantize,
+                  select_hypothesis, config)
 from .patch import patch_reference
 
 __all__ = ["ball_query", "knn_points", "knn_gather", "knn1_transfer", "ume_moments", "my_ume_generation",
@@ -18,4 +19,5 @@ __all__ = ["ball_query", "knn_points", "knn_gather", "knn1_transfer", "ume_momen
            "batch_estimate_transform_ume_old", "relative_rotation_error", "ball_query_gather", "ume_kp_layer",
            "register_hypotheses", "feature_spatial_var", "cauchy_kernel", "correlation_scores",
            "pc_corr_cost_pytorch3d", "weighted_features", "FeatureCorrelator", "weighted_match_subsample",
+           "sparse_quantize", "select_hypothesis",
            "patch_reference", "config"]

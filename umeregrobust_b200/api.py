@@ -494,6 +494,64 @@ class FeatureCorrelator:
         return T_kp[best]
 
 
+# ----------------------------------------------------------------------------- voxel de-duplication (f4)
+def sparse_quantize(coordinates, features=None, return_index=False, quantization_size=None):
+    """MinkowskiEngine `ME.utils.sparse_quantize` as evaluate.py:261-264 calls it: integer voxel
+    coordinates floor(coordinates / quantization_size) with duplicates removed — the first row of
+    every occupied voxel survives, survivors keep their row order.  coordinates (N,3) float32 on
+    the device.  Returns `unique_coords (M,3) int32` and, with return_index=True, the surviving
+    rows `(M,) int64` (ascending).  Reading M back is a sync point, as in the reference."""
+    if features is not None:
+        raise NotImplementedError("sparse_quantize: the feature-averaging mode is not used by evaluate.py")
+    if quantization_size is None:
+        quantization_size = 1.0
+    c = _dev_f32(coordinates, "coordinates", 2)
+    if c.shape[1] != 3:
+        raise ValueError("sparse_quantize: coordinates must be (N,3)")
+    N = c.shape[0]
+    index = torch.empty((max(N, 1),), dtype=torch.int64, device=c.device)
+    coords = torch.empty((max(N, 1), 3), dtype=torch.int32, device=c.device)
+    count = torch.empty((1,), dtype=torch.int32, device=c.device)
+    with torch.cuda.device(c.device):
+        L = _lib.lib()
+        ws = _workspace(L.ume_voxel_unique_workspace_bytes(N), c.device)
+        rc = L.ume_voxel_unique_f32(_ptr(c), N, float(quantization_size), _ptr(index), _ptr(coords), _ptr(count),
+                                    _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "sparse_quantize")
+    M = int(count.item())
+    if M < 0:
+        raise ValueError("sparse_quantize: a coordinate is NaN or outside +-2^20 voxels")
+    return (coords[:M], index[:M]) if return_index else coords[:M]
+
+
+def select_hypothesis(src_pts_raw, tgt_pts_raw, src_pts, tgt_pts, src_feat, tgt_feat, hypotheses, corr_sigma,
+                      corr_ds=0.3, tgt_ds=0.3, pc_corr_max_size=30000, corr_num_nn=20, src_rows=None, tgt_rows=None,
+                      generator=None):
+    """evaluate.py:259-296 for one pair, stream-ordered on the device: voxel de-duplication of the
+    raw clouds (:261-264), nearest-row feature transfer from the voxel clouds the backbone saw
+    (:272-275), random down-sampling to `pc_corr_max_size` (:278-285) and the correlator's pick
+    among the hypotheses (pc_fcht :20-47).
+      src_pts_raw (Nr,3), tgt_pts_raw (Nr',3): raw clouds; src_pts (1,N,3), src_feat (1,N,C) (and
+      tgt_*): the clouds the features live on; hypotheses (n_hyp,4,4).
+      src_rows / tgt_rows: the down-sampling draw as data (the reference uses the host RNG,
+      np.random.choice, which cannot be reproduced bit for bit); default: torch.randperm.
+    Returns (T (4,4), best index (0-dim int64), scores (n_hyp,))."""
+    def prep(raw, q, pts, feat, rows):
+        raw = _dev_f32(raw, "raw cloud", 2)
+        _, keep = sparse_quantize(raw, return_index=True, quantization_size=q)
+        ds = raw[keep][None]
+        f = knn1_transfer(ds, pts, feat)
+        n = min(int(pc_corr_max_size), ds.shape[1])
+        if rows is None:
+            rows = torch.randperm(ds.shape[1], device=ds.device, generator=generator)[:n]
+        return ds[:, rows].contiguous(), f[:, rows].contiguous()
+    sp, sf = prep(src_pts_raw, corr_ds, src_pts, src_feat, src_rows)
+    tp, tf = prep(tgt_pts_raw, tgt_ds, tgt_pts, tgt_feat, tgt_rows)
+    corr = FeatureCorrelator(sigma=corr_sigma, corr_num_nn=corr_num_nn)
+    score, best = corr.scores(sp, tp, sf, tf, hypotheses)
+    return hypotheses[best], best, score
+
+
 # ----------------------------------------------------------------------------- match sub-sampling (f2)
 def weighted_match_subsample(ume_d, tau, num_samples, generator=None):
     """Device-side equivalent of evaluate.py:233-245: draw `num_samples` of the n matches WITHOUT
