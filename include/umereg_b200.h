@@ -43,6 +43,9 @@ typedef enum ume_status {
                                       pytorch3d's CUDA kernel); default: separately rounded mul/add
                                       (pytorch3d CPU build, torch/numpy restatements)           */
 #define UME_FLAG_CELL_DIV2     2u  /* search grid with cell = radius/2 instead of radius        */
+#define UME_FLAG_RAW_MOMENTS   8u  /* ume_moments_f32: F = [sum f | sum f x^T] without the division of
+                                      evaluate.py:59 (training path: utils/loc_utils.py:157-161 with
+                                      normalized_ume=False, and the differentiable wrapper)          */
 #define UME_FLAG_CTA_MOMENTS   4u  /* ume_moments_f32: force the CTA-per-keypoint kernel (the default
                                       for C in {16,32,64,128} is the warp-per-keypoint kernel)      */
 
@@ -78,6 +81,24 @@ size_t ume_moments_workspace_bytes(int B, int N, int n, int C, int K);
 int ume_moments_f32(const float* pts, const float* kpts, const float* feat, int B, int N, int n,
                     int C, int K, float radius, unsigned flags, float* F, float* Fc, int32_t* count,
                     void* ws, size_t ws_bytes, void* stream);
+
+/* Gradient of the RAW moments with respect to the features (the backward pass of the
+ * training-time UME generation, utils/loc_utils.py:86-188, which the reference gets from autograd
+ * through its materialised (B,n,K,C) gather):
+ *   grad_feat[b,j,c] += sum over keypoints i whose neighbourhood holds row j of
+ *                       gF[b,i,c,0] + gF[b,i,c,1:4] . pts[b,j,:]
+ * Same neighbourhoods as ume_moments_f32 with the same (K, radius, flags); grad_feat (B,N,C) must be
+ * initialised by the caller (it is accumulated into with vector atomics, so the last bits depend
+ * on the order of arrival).  C in {16,32,64,128}. */
+int ume_moments_backward_f32(const float* pts, const float* kpts, const float* gF, int B, int N, int n, int C,
+                             int K, float radius, unsigned flags, float* grad_feat, void* ws, size_t ws_bytes,
+                             void* stream);
+
+/* count[b,i] = min(K, number of rows of pts[b] with dist2 < radius^2 from kpts[b,i]) without building
+ * anything else: the dense-neighbourhood filter of utils/loc_utils.py:119 ((bq_idxs > -1).sum >= min_nn)
+ * without the (B,n,K) index tensor.  Workspace: ume_moments_workspace_bytes. */
+int ume_neighbor_count_f32(const float* pts, const float* kpts, int B, int N, int n, int K, float radius,
+                           unsigned flags, int32_t* count, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- subspace descriptor
  * Replaces the two torch.linalg.qr calls of utils/loc_utils.py:9,11 (and :338,341): an

@@ -64,6 +64,23 @@ def ume_moments(pts, kpts, feat, K, radius, dtype=np.float32, fma=False, use_c=T
     return (F, idx) if return_idx else F
 
 
+def ume_moments_backward(pts, kpts, grad_F, K, radius, dtype=np.float64, fma=False):
+    """Gradient of the RAW moments F[i,c,:] = sum_{j in nbr(i)} feat[j,c] [1, pts[j]] with respect to
+    feat: what torch autograd returns through the gather + matmul of utils/loc_utils.py:150-161.
+    grad_F (B,n,C,4) -> (B,N,C)."""
+    pts32 = np.ascontiguousarray(pts, dtype=np.float32)
+    kp32 = np.ascontiguousarray(kpts, dtype=np.float32)
+    idx = p3d.ball_query_c(kp32, pts32, K, radius, return_nn=False, fma=fma).idx
+    B, N, _ = pts32.shape
+    g = np.asarray(grad_F, dtype=dtype)
+    out = np.zeros((B, N, g.shape[2]), dtype=dtype)
+    for b in range(B):
+        for i in range(idx.shape[1]):
+            rows = idx[b, i][idx[b, i] >= 0]
+            out[b, rows] += g[b, i, :, 0][None] + pts32[b, rows].astype(dtype) @ g[b, i, :, 1:].T
+    return out
+
+
 def normaliser_condition(feat, idx):
     """kappa[b,i] = sum|f| / |sum f + 1e-6| over keypoint i's neighbourhood: how much the division at
     evaluate.py:59 amplifies rounding (features are signed, so the sum cancels; SURVEY §7 'Normaliser

@@ -1,0 +1,105 @@
+"""GPU parity of the training-time row: differentiable UME generation (CUDA forward,
+CUDA scatter backward) and the two UME losses against golden vectors produced by the reference's own
+`generate_ume_from_keypoints2` / `UMEContrastiveLoss` / `CubeRegistrationLoss` on CPU torch
+(tests/golden/make_golden_training.py), and against the oracle at a larger size."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import ume_oracle as orc
+from umeregrobust_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ume():
+    import umeregrobust_b200 as u
+    from umeregrobust_b200 import _lib
+    _lib.lib()
+    return u
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, b, rel):
+    return float(np.abs(a - b).max()) <= rel * max(float(np.abs(b).max()), 1e-30)
+
+
+@pytest.mark.parametrize("C,K", [(32, 300), (64, 50), (16, 2000), (128, 120)])
+def test_moments_backward_matches_oracle(ume, C, K):
+    rng = np.random.default_rng(C + K)
+    N, n = 6000, 96
+    pts = (np.stack([rng.uniform(-12, 12, (2, N)), rng.uniform(-12, 12, (2, N)), rng.uniform(-1, 1, (2, N))], -1)
+           + np.array([20.0, 5.0, 0.0])).astype(np.float32)
+    kp = pts[:, rng.choice(N, n, replace=False)].copy()
+    gF = rng.normal(size=(2, n, C, 4)).astype(np.float32)
+    got = host(ume.ume_moments_backward(dev(pts), dev(kp), dev(gF), K, 4.0))
+    ref = orc.ume_moments_backward(pts, kp, gF, K, 4.0)
+    assert close(got, ref, 2e-5)
+    cnt = host(ume.neighbor_count(dev(pts), dev(kp), K, 4.0))
+    idx = orc.ume_moments(pts, kp, np.zeros((2, N, 4), np.float32), K, 4.0, return_idx=True)[1]
+    assert np.array_equal(cnt, (idx >= 0).sum(-1))
+    # raw forward = un-normalised moments; autograd wrapper: d/dfeat sum(F * gF) is exactly the kernel above
+    from umeregrobust_b200 import training
+    feat = dev(synth._normalize_rows(rng.normal(size=(2, N, C))).astype(np.float32)).requires_grad_(True)
+    F = training.ume_moments_autograd(dev(pts), dev(kp), feat, K, 4.0, normalized=False)
+    (F * dev(gF)).sum().backward()
+    assert close(host(feat.grad), ref, 2e-5)
+    Fn = host(ume.ume_moments(dev(pts), dev(kp), feat.detach(), K, 4.0))
+    Fr = host(F)
+    assert close(Fr / (Fr[..., :1].sum(-2, keepdims=True) + 1e-6), Fn, 1e-5)
+
+
+def test_generate_ume_from_keypoints2_against_reference_golden(ume, golden):
+    from umeregrobust_b200 import training
+    g = golden("training")
+    kw = dict(nn_r=float(g["kw_nn_r"]), max_nn=int(g["kw_max_nn"]), min_nn=int(g["kw_min_nn"]),
+              num_samples=int(g["kw_num_samples"]), flat_labels=[int(v) for v in g["kw_flat_labels"]],
+              nn_intersection_r=float(g["kw_nn_intersection_r"]))
+    for norm in (False, True):
+        tag = "norm_" if norm else "raw_"
+        vf = dev(g["velo_feat"]).requires_grad_(True)
+        rf = dev(g["ref_feat"]).requires_grad_(True)
+        F_v, F_r, kp_v, kp_r, ratio, cond = training.generate_ume_from_keypoints2(
+            dev(g["velo_pts"]), dev(g["velo_seg"]), vf, dev(g["ref_pts"]), rf, dev(g["gt_tform"]), normalized_ume=norm, **kw)
+        assert np.array_equal(host(kp_v), g[tag + "kp_velo"])                     # the same keypoints, same order
+        assert np.abs(host(kp_r) - g[tag + "kp_ref"]).max() < 1e-5
+        assert np.array_equal(host(cond), g[tag + "cond"])
+        assert close(host(F_v), g[tag + "F_velo"], 2e-5) and close(host(F_r), g[tag + "F_ref"], 2e-5)
+        assert np.abs(host(ratio) - g[tag + "ratio"]).max() <= 1.01 / kw["max_nn"]   # one boundary neighbour at most
+        if not norm:
+            w1 = dev(np.random.default_rng(1).normal(size=tuple(F_v.shape)).astype(np.float32))
+            w2 = dev(np.random.default_rng(2).normal(size=tuple(F_r.shape)).astype(np.float32))
+            ((F_v * w1).sum() + (F_r * w2).sum()).backward()
+            assert close(host(vf.grad), g["raw_grad_velo_feat"], 1e-4)
+            assert close(host(rf.grad), g["raw_grad_ref_feat"], 1e-4)
+
+
+def test_ume_losses_against_reference_golden(ume, golden):
+    # train_coloring.py:48-58: UMEContrastiveLoss + CubeRegistrationLoss, values and d/dfeat
+    from umeregrobust_b200 import training
+    g = golden("training")
+    n_s, K, mn, r, ri = int(g["kw_num_samples"]), int(g["kw_max_nn"]), int(g["kw_min_nn"]), float(g["kw_nn_r"]), float(g["kw_nn_intersection_r"])
+    vf = dev(g["velo_feat"]).requires_grad_(True)
+    rf = dev(g["ref_feat"]).requires_grad_(True)
+    ume_fn = training.UMEContrastiveLoss(num_samples=n_s, max_nn=K, min_nn=mn, nn_r=r, tau=0.1, tau_neg=0.1, flat_labels=[9],
+                                         nn_intersection_r=ri)
+    reg_fn = training.CubeRegistrationLoss(rtume_max_nn=K, rtume_r_nn=r, cube_scale=1.0, nn_inter_ratio_thr=0.5)
+    gt = dev(g["gt_tform"])
+    ume_loss, kp_v, kp_r, U_v, U_r, ratio, valid = ume_fn(dev(g["velo_pts"]), dev(g["velo_seg"]), vf, dev(g["ref_pts"]), rf, gt)
+    reg_loss, rre, rte = reg_fn(dev(g["velo_pts"]), U_v, dev(g["ref_pts"]), U_r, gt, ratio, valid)
+    assert close(host(U_v), g["loss_ume_velo"], 2e-5) and close(host(U_r), g["loss_ume_ref"], 2e-5)
+    assert abs(float(ume_loss) - float(g["ume_loss"])) < 2e-3 * abs(float(g["ume_loss"])) + 1e-6
+    assert abs(float(reg_loss) - float(g["reg_loss"])) < 2e-3 * abs(float(g["reg_loss"]))
+    assert np.abs(host(rte) - g["loss_rte"]).max() < 2e-3 * np.abs(g["loss_rte"]).max()
+    (ume_loss + reg_loss).backward()
+    assert close(host(vf.grad), g["loss_grad_velo_feat"], 5e-3)
+    assert close(host(rf.grad), g["loss_grad_ref_feat"], 5e-3)

@@ -185,3 +185,27 @@ def test_sparse_quantize_known_answer():
     assert np.all(np.diff(idx) > 0) and len(np.unique(vox, axis=0)) == len(vox)
     # idempotent: the survivors are all distinct voxels
     assert len(orc.sparse_quantize(pts[idx], 1.0)[1]) == len(idx)
+
+
+def test_moments_backward_against_reference_autograd(golden):
+    # the reference's autograd gradient of sum(F_velo * w1) + sum(F_ref * w2) through its materialised
+    # gather (tests/golden/make_golden_training.py) vs the oracle's closed form
+    g = golden("training")
+    K, r = int(g["kw_max_nn"]), float(g["kw_nn_r"])
+    for side, seed in (("velo", 1), ("ref", 2)):
+        F = g["raw_F_" + side]
+        w = np.random.default_rng(seed).normal(size=F.shape).astype(np.float32)
+        pts = g["velo_pts"] if side == "velo" else g["ref_pts"]
+        feat = g["velo_feat"] if side == "velo" else g["ref_feat"]
+        got = orc.ume_moments_backward(pts, g["raw_kp_" + side], w, K, r)
+        ref = g["raw_grad_%s_feat" % side]
+        assert np.abs(got - ref).max() < 1e-4 * np.abs(ref).max()
+        # the reference's raw (un-normalised) moments from the oracle's neighbour sets
+        idx = orc.ume_moments(pts, g["raw_kp_" + side], feat, K, r, return_idx=True)[1]
+        fp = np.concatenate([feat, np.zeros_like(feat[:, :1])], 1).astype(np.float64)
+        pp = np.concatenate([pts, np.zeros_like(pts[:, :1])], 1).astype(np.float64)
+        safe = np.where(idx < 0, pts.shape[1], idx)
+        for b in range(F.shape[0]):
+            nf, npt = fp[b][safe[b]], pp[b][safe[b]]
+            Fr = np.concatenate([nf.sum(1)[..., None], np.einsum("nkc,nkd->ncd", nf, npt)], -1)
+            assert np.abs(Fr - F[b]).max() < 2e-5 * np.abs(F[b]).max()

@@ -20,6 +20,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 UME_FLAG_FMA_DIST = 1
 UME_FLAG_CELL_DIV2 = 2
 UME_FLAG_CTA_MOMENTS = 4
+UME_FLAG_RAW_MOMENTS = 8
 
 _lock = threading.Lock()
 _lib = None
@@ -85,6 +86,8 @@ def _bind(lib):
         "ume_ball_query_f32": (i32, [vp, vp, i32, i32, i32, i32, f32, u32, vp, vp, vp, vp, vp, sz, vp]),
         "ume_moments_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
         "ume_moments_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, u32, vp, vp, vp, vp, sz, vp]),
+        "ume_moments_backward_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, u32, vp, vp, sz, vp]),
+        "ume_neighbor_count_f32": (i32, [vp, vp, i32, i32, i32, i32, f32, u32, vp, vp, sz, vp]),
         "ume_orthonormalize_f32": (i32, [vp, i64, i32, vp, vp, vp]),
         "ume_cdist_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
         "ume_cdist_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]),
@@ -117,7 +120,8 @@ EXPORTED_SYMBOLS = ["ume_abi_version", "ume_last_error", "ume_status_string", "u
                     "ume_knn1_gather_f32", "ume_knn_workspace_bytes", "ume_knn_f32",
                     "ume_feature_spatial_var_workspace_bytes", "ume_feature_spatial_var_f32", "ume_weight_features_f32",
                     "ume_corr_scores_workspace_bytes", "ume_corr_scores_f32",
-                    "ume_voxel_unique_workspace_bytes", "ume_voxel_unique_f32"]
+                    "ume_voxel_unique_workspace_bytes", "ume_voxel_unique_f32",
+                    "ume_moments_backward_f32", "ume_neighbor_count_f32"]
 
 
 def lib():

@@ -170,10 +170,11 @@ def knn1_transfer(q, p, x):
 
 
 # ----------------------------------------------------------------------------- UME moments
-def ume_moments(pts, kpts, feat, K, radius, return_centered=False, return_count=False, buf=None, tag=""):
+def ume_moments(pts, kpts, feat, K, radius, return_centered=False, return_count=False, buf=None, tag="", raw=False):
     """Fused ball-query + gather + moment build.  F (B,n,C,4) exactly as evaluate.py:50-60
     produces it; optionally the keypoint-centred matrix Fc (same column space) and the
-    neighbour count per keypoint."""
+    neighbour count per keypoint.  raw=True leaves out the normalisation of evaluate.py:59
+    (utils/loc_utils.py:157-161 with normalized_ume=False; C in {16,32,64,128})."""
     pts = _dev_f32(pts, "pts", 3)
     kpts = _dev_f32(kpts, "kpts", 3)
     feat = _dev_f32(feat, "feat", 3)
@@ -189,7 +190,8 @@ def ume_moments(pts, kpts, feat, K, radius, return_centered=False, return_count=
     with torch.cuda.device(dev):
         L = _lib.lib()
         ws = _workspace(L.ume_moments_workspace_bytes(B, N, n, C, int(K)), dev)
-        rc = L.ume_moments_f32(_ptr(pts), _ptr(kpts), _ptr(feat), B, N, n, C, int(K), float(radius), _flags(),
+        rc = L.ume_moments_f32(_ptr(pts), _ptr(kpts), _ptr(feat), B, N, n, C, int(K), float(radius),
+                               _flags() | (_lib.UME_FLAG_RAW_MOMENTS if raw else 0),
                                _ptr(F), _ptr(Fc), _ptr(cnt), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "ume_moments")
     out = (F,)
@@ -198,6 +200,44 @@ def ume_moments(pts, kpts, feat, K, radius, return_centered=False, return_count=
     if return_count:
         out += (cnt,)
     return out[0] if len(out) == 1 else out
+
+
+def ume_moments_backward(pts, kpts, grad_F, K, radius):
+    """Gradient of the RAW moments with respect to the features: the same
+    neighbourhoods as `ume_moments(pts, kpts, ., K, radius)`, every neighbour row j of keypoint i
+    receives grad_F[i,c,0] + grad_F[i,c,1:4] . pts[j].  grad_F (B,n,C,4) -> (B,N,C)."""
+    pts = _dev_f32(pts, "pts", 3)
+    kpts = _dev_f32(kpts, "kpts", 3)
+    g = _dev_f32(grad_F, "grad_F", 4)
+    B, N, _ = pts.shape
+    n, C = kpts.shape[1], g.shape[2]
+    if tuple(g.shape) != (B, n, C, 4):
+        raise ValueError("ume_moments_backward: grad_F %s does not match (B,n,C,4)" % (tuple(g.shape),))
+    out = torch.zeros((B, N, C), dtype=torch.float32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        L = _lib.lib()
+        ws = _workspace(L.ume_moments_workspace_bytes(B, N, n, C, int(K)), pts.device)
+        rc = L.ume_moments_backward_f32(_ptr(pts), _ptr(kpts), _ptr(g), B, N, n, C, int(K), float(radius), _flags(),
+                                        _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "ume_moments_backward")
+    return out
+
+
+def neighbor_count(pts, kpts, K, radius):
+    """min(K, number of rows of pts within `radius` of each keypoint) -> (B,n) int32, without the
+    (B,n,K) index tensor ((ball_query(...).idx > -1).sum(-1) as used at utils/loc_utils.py:103,119)."""
+    pts = _dev_f32(pts, "pts", 3)
+    kpts = _dev_f32(kpts, "kpts", 3)
+    B, N, _ = pts.shape
+    n = kpts.shape[1]
+    cnt = torch.zeros((B, n), dtype=torch.int32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        L = _lib.lib()
+        ws = _workspace(L.ume_moments_workspace_bytes(B, N, n, 32, int(K)), pts.device)
+        rc = L.ume_neighbor_count_f32(_ptr(pts), _ptr(kpts), B, N, n, int(K), float(radius), _flags(), _ptr(cnt),
+                                      _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "neighbor_count")
+    return cnt
 
 
 def my_ume_generation(pts, kpts, feat, args):

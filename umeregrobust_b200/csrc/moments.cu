@@ -285,20 +285,19 @@ extern "C" int ume_moments_f32(const float* pts, const float* kpts, const float*
     p.n = n; p.C = C; p.K = K; p.cap = moments_cap(C, K); p.radius = radius;
     const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
     const bool aligned = reinterpret_cast<uintptr_t>(feat) % 16 == 0;
-    if (!(flags & UME_FLAG_CTA_MOMENTS) && aligned && (C == 16 || C == 32 || C == 64 || C == 128)) {
+    const bool warp_ok = aligned && (C == 16 || C == 32 || C == 64 || C == 128);
+    const bool raw = (flags & UME_FLAG_RAW_MOMENTS) != 0;
+    UME_REQUIRE(!raw || warp_ok, UME_ERR_UNSUPPORTED, "ume_moments_f32: raw moments need C in {16,32,64,128} (C = %d)", C);
+    if ((!(flags & UME_FLAG_CTA_MOMENTS) || raw) && warp_ok) {
         // one warp per keypoint (moments_warp.cuh): the default for the channel counts it is built for
         warpk::Params wp;
         wp.grid = p.grid; wp.kpts = kpts; wp.feat = feat; wp.F = F; wp.Fc = Fc; wp.count = count;
+        wp.gF = nullptr; wp.grad_feat = nullptr; wp.raw = raw ? 1 : 0;
         wp.n = n; wp.K = K; wp.total = (long long)B * n; wp.radius = radius;
         wp.next = w.take<unsigned long long>(1);
         UME_REQUIRE(w.ok(), UME_ERR_WORKSPACE, "ume_moments_f32: workspace too small for the work counter");
         ProfScope prof(UME_PROF_MOMENTS, stream);
-        switch (C) {
-            case 16: return warpk::launch<4>(wp, fma, stream);
-            case 32: return warpk::launch<8>(wp, fma, stream);
-            case 64: return warpk::launch<16>(wp, fma, stream);
-            default: return warpk::launch<32>(wp, fma, stream);
-        }
+        return warpk::launch_c<warpk::kForward>(wp, C, fma, stream);
     }
     const bool vec = (C % 4 == 0) && ((C & (C - 1)) == 0) && C >= 4 && C <= 128 &&
                      (reinterpret_cast<uintptr_t>(feat) % 16 == 0);
@@ -316,4 +315,49 @@ extern "C" int ume_moments_f32(const float* pts, const float* kpts, const float*
     if (C <= 64) return launch_moments<GenAcc<2>>(p, B, fma, stream);
     if (C <= 128) return launch_moments<GenAcc<4>>(p, B, fma, stream);
     return launch_moments<GenAcc<8>>(p, B, fma, stream);
+}
+
+// Shared front end of the two auxiliary entry points below (same checks and grid as ume_moments_f32).
+static int moments_aux(const float* pts, const float* kpts, const float* gF, int B, int N, int n, int C, int K,
+                       float radius, unsigned flags, float* grad_feat, int32_t* count, void* ws, size_t ws_bytes,
+                       void* stream_, bool backward, const char* who) {
+    using namespace ume;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    UME_REQUIRE(B >= 0 && N >= 0 && n >= 0, UME_ERR_BAD_ARG, "%s: negative size", who);
+    if (B == 0 || n == 0) return UME_OK;
+    UME_REQUIRE(pts && kpts, UME_ERR_BAD_ARG, "%s: null pointer", who);
+    UME_REQUIRE(N >= 1 && K >= 1, UME_ERR_BAD_ARG, "%s: N = %d, K = %d", who, N, K);
+    UME_REQUIRE(N <= kMaxPoints && (size_t)B * n < 0x7fffffffull, UME_ERR_UNSUPPORTED, "%s: size not supported", who);
+    UME_REQUIRE(ws && ws_bytes >= ume_moments_workspace_bytes(B, N, n, C, K), UME_ERR_WORKSPACE, "%s: workspace too small", who);
+    Workspace w(ws, ws_bytes);
+    warpk::Params wp;
+    int rc = grid_build(pts, kpts, B, N, n, fabsf(radius), fabsf(radius) / ((flags & UME_FLAG_CELL_DIV2) ? 2.f : 1.f), kCellsCap, w, &wp.grid, stream);
+    if (rc != UME_OK) return rc;
+    wp.kpts = kpts; wp.feat = nullptr; wp.F = nullptr; wp.Fc = nullptr; wp.count = count;
+    wp.gF = gF; wp.grad_feat = grad_feat; wp.raw = 1;
+    wp.n = n; wp.K = K; wp.total = (long long)B * n; wp.radius = radius;
+    wp.next = w.take<unsigned long long>(1);
+    UME_REQUIRE(w.ok(), UME_ERR_WORKSPACE, "%s: workspace too small for the work counter", who);
+    const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
+    ProfScope prof(UME_PROF_MOMENTS, stream);
+    return backward ? warpk::launch_c<warpk::kBackward>(wp, C, fma, stream)
+                    : warpk::launch_c<warpk::kCountOnly>(wp, 32, fma, stream);
+}
+
+extern "C" int ume_moments_backward_f32(const float* pts, const float* kpts, const float* gF, int B, int N, int n, int C,
+                                        int K, float radius, unsigned flags, float* grad_feat, void* ws, size_t ws_bytes,
+                                        void* stream) {
+    UME_REQUIRE(gF && grad_feat, UME_ERR_BAD_ARG, "ume_moments_backward_f32: null pointer");
+    UME_REQUIRE((C == 16 || C == 32 || C == 64 || C == 128) && reinterpret_cast<uintptr_t>(grad_feat) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(gF) % 16 == 0,
+                UME_ERR_UNSUPPORTED, "ume_moments_backward_f32: C = %d must be 16, 32, 64 or 128 (16-byte aligned rows)", C);
+    return moments_aux(pts, kpts, gF, B, N, n, C, K, radius, flags, grad_feat, nullptr, ws, ws_bytes, stream, true,
+                       "ume_moments_backward_f32");
+}
+
+extern "C" int ume_neighbor_count_f32(const float* pts, const float* kpts, int B, int N, int n, int K, float radius,
+                                      unsigned flags, int32_t* count, void* ws, size_t ws_bytes, void* stream) {
+    UME_REQUIRE(count, UME_ERR_BAD_ARG, "ume_neighbor_count_f32: null pointer");
+    return moments_aux(pts, kpts, nullptr, B, N, n, 32, K, radius, flags, nullptr, count, ws, ws_bytes, stream, false,
+                       "ume_neighbor_count_f32");
 }

@@ -42,6 +42,11 @@ namespace warpk {
 #ifndef UME_WARPK_UNROLL
 #define UME_WARPK_UNROLL 4         // feature-row loads in flight per lane
 #endif
+#if UME_WARPK_PERSISTENT
+#define UME_WARPK_NEXT continue
+#else
+#define UME_WARPK_NEXT break
+#endif
 constexpr int kWarps = UME_WARPK_WARPS;
 constexpr int kChunks = 128;       // chunk-table window per warp
 constexpr int kBins = 256;
@@ -66,7 +71,10 @@ struct Params {
     float* F;             // (B,n,C,4)
     float* Fc;            // (B,n,C,4) or null
     int32_t* count;       // (B,n) or null
-    unsigned long long* next;   // work counter (zeroed before the launch)
+    unsigned long long* next;   // work counter (zeroed before the launch; persistent builds only)
+    const float* gF;      // kBackward: (B,n,C,4) gradient of the RAW moments [sum f | sum f x^T]
+    float* grad_feat;     // kBackward: (B,N,C), accumulated into
+    int raw;              // kForward: 1 = leave out the normalisation of evaluate.py:59
     int n, K;
     long long total;      // B*n
     float radius;
@@ -148,7 +156,18 @@ UME_DEVI void scan(WarpSmem& sm, int nrows, int nchunks, int& loaded_w0, const f
     }
 }
 
-template <int LPR, bool kFma>
+enum Mode { kForward = 0, kBackward = 1, kCountOnly = 2 };
+
+UME_DEVI void red_add_f4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// MODE kForward : F (and Fc, count) as documented in include/umereg_b200.h
+//      kBackward: the same neighbourhoods, walked the same way; instead of reading a neighbour's
+//                 feature row the warp adds  gF[i,c,0] + gF[i,c,1:4] . x_j  to grad_feat[j,c]
+//                 (d/df of the raw moments; 8 lanes x RED.128 per row)
+//      kCountOnly: pass 1 only -> count
+template <int LPR, bool kFma, int MODE>
 __global__ void __launch_bounds__(32 * kWarps, UME_WARPK_MINB) moments_warp_kernel(Params p) {
     constexpr int C = 4 * LPR;
     constexpr int RPW = 32 / LPR;                 // feature rows per warp instruction
@@ -279,11 +298,35 @@ __global__ void __launch_bounds__(32 * kWarps, UME_WARPK_MINB) moments_warp_kern
         }
     }
 
-    // ---- pass 2: gather + moments
+    if (MODE == kCountOnly) {
+        if (lane == 0 && p.count) p.count[q] = min(hits, K);
+        UME_WARPK_NEXT;
+    }
+
+    // ---- pass 2: gather + moments (kBackward: scatter of the moment gradients)
     float2 a01[4], a23[4];                         // [moment 1,x,y,z] of channels (0,1) and (2,3) of this lane
 #pragma unroll
     for (int j = 0; j < 4; ++j) { a01[j] = make_float2(0.f, 0.f); a23[j] = make_float2(0.f, 0.f); }
     const float* fl = feat_b + 4 * l;
+    float* gl = nullptr;
+    if (MODE == kBackward) {
+        // a01[j] / a23[j] hold the gradient instead: [g0 + g1 . k, g1x, g1y, g1z] per channel, so that
+        // d/df_j = a[0] + a[1] ex + a[2] ey + a[3] ez with e = x_j - k
+        gl = p.grad_feat + (size_t)b * N * C + 4 * l;
+        const float4* g = reinterpret_cast<const float4*>(p.gF) + (size_t)q * C + 4 * l;
+        const float4 g0 = __ldg(g + 0), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3);
+        auto c0 = [&](const float4& v) { return fmaf(v.w, kz, fmaf(v.z, ky, fmaf(v.y, kx, v.x))); };
+        a01[0] = make_float2(c0(g0), c0(g1)); a23[0] = make_float2(c0(g2), c0(g3));
+        a01[1] = make_float2(g0.y, g1.y);     a23[1] = make_float2(g2.y, g3.y);
+        a01[2] = make_float2(g0.z, g1.z);     a23[2] = make_float2(g2.z, g3.z);
+        a01[3] = make_float2(g0.w, g1.w);     a23[3] = make_float2(g2.w, g3.w);
+    }
+    auto scatter = [&](const float4& nb) {
+        const float2 nx = make_float2(nb.x, nb.x), ny = make_float2(nb.y, nb.y), nz = make_float2(nb.z, nb.z);
+        const float2 v01 = __ffma2_rn(a01[3], nz, __ffma2_rn(a01[2], ny, __ffma2_rn(a01[1], nx, a01[0])));
+        const float2 v23 = __ffma2_rn(a23[3], nz, __ffma2_rn(a23[2], ny, __ffma2_rn(a23[1], nx, a23[0])));
+        red_add_f4(gl + (size_t)__float_as_int(nb.w) * C, v01.x, v01.y, v23.x, v23.y);
+    };
     auto accumulate = [&](const float4& nb, const float4& f) {
         const float2 f01 = make_float2(f.x, f.y), f23 = make_float2(f.z, f.w);
         const float2 nx = make_float2(nb.x, nb.x), ny = make_float2(nb.y, nb.y), nz = make_float2(nb.z, nb.z);
@@ -301,11 +344,16 @@ __global__ void __launch_bounds__(32 * kWarps, UME_WARPK_MINB) moments_warp_kern
             // a batch never wraps: RPW * U divides kRing.  Row indices first, all U feature loads in
             // flight, then the offsets are re-read from the ring as the rows arrive (registers)
             const unsigned ra = ring_sub + 16u * (unsigned)(rpos & (kRing - 1));
-            float4 f[U];
+            if (MODE == kBackward) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) f[u] = ldg_f4(fl + (size_t)lds_u32(ra + 16u * (u * RPW) + 12u) * C);
+                for (int u = 0; u < U; ++u) scatter(lds_f4(ra + 16u * (u * RPW)));
+            } else {
+                float4 f[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) accumulate(lds_f4(ra + 16u * (u * RPW)), f[u]);
+                for (int u = 0; u < U; ++u) f[u] = ldg_f4(fl + (size_t)lds_u32(ra + 16u * (u * RPW) + 12u) * C);
+#pragma unroll
+                for (int u = 0; u < U; ++u) accumulate(lds_f4(ra + 16u * (u * RPW)), f[u]);
+            }
             rpos += RPW * U;
         }
     };
@@ -348,9 +396,11 @@ __global__ void __launch_bounds__(32 * kWarps, UME_WARPK_MINB) moments_warp_kern
         const int e = rpos + sub;
         if (e < wpos) {
             const float4 nb = lds_f4(ring_a + 16u * (unsigned)(e & (kRing - 1)));
-            accumulate(nb, ldg_f4(fl + (size_t)__float_as_int(nb.w) * C));
+            if (MODE == kBackward) scatter(nb);
+            else accumulate(nb, ldg_f4(fl + (size_t)__float_as_int(nb.w) * C));
         }
     }
+    if (MODE == kBackward) UME_WARPK_NEXT;
 
     // ---- combine the RPW row groups, normalise, un-centre, store
     float acc[4][4];                               // [channel within lane][moment]
@@ -365,7 +415,7 @@ __global__ void __launch_bounds__(32 * kWarps, UME_WARPK_MINB) moments_warp_kern
     float f0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
 #pragma unroll
     for (int o = 1; o < LPR; o <<= 1) f0 += __shfl_xor_sync(UME_FULL_MASK, f0, o);
-    const float den = f0 + 1e-6f;                  // evaluate.py:59
+    const float den = p.raw ? 1.f : f0 + 1e-6f;    // evaluate.py:59
     if (lane < LPR) {
         float4* Fo = reinterpret_cast<float4*>(p.F) + (size_t)q * C + 4 * lane;
         float4* Fco = p.Fc ? reinterpret_cast<float4*>(p.Fc) + (size_t)q * C + 4 * lane : nullptr;
@@ -384,9 +434,11 @@ __global__ void __launch_bounds__(32 * kWarps, UME_WARPK_MINB) moments_warp_kern
   }
 }
 
-template <int LPR>
+template <int LPR, int MODE>
 int launch(const Params& p, bool fma, cudaStream_t stream) {
-    auto kern = fma ? moments_warp_kernel<LPR, true> : moments_warp_kernel<LPR, false>;
+    auto kern = fma ? moments_warp_kernel<LPR, true, MODE> : moments_warp_kernel<LPR, false, MODE>;
+    long long grid = (p.total + kWarps - 1) / kWarps;
+#if UME_WARPK_PERSISTENT
     static int ctas_per_sm[2] = {0, 0}, sms = 0;   // per template instance; benign race (same values)
     if (!ctas_per_sm[fma]) {
         int dev = 0, n = 0, per = 0;
@@ -397,13 +449,23 @@ int launch(const Params& p, bool fma, cudaStream_t stream) {
         sms = n;
         ctas_per_sm[fma] = per;
     }
-    const long long want = (p.total + kWarps - 1) / kWarps;
-    const long long grid = (!UME_WARPK_PERSISTENT || want < (long long)sms * ctas_per_sm[fma]) ? want : (long long)sms * ctas_per_sm[fma];
+    if (grid > (long long)sms * ctas_per_sm[fma]) grid = (long long)sms * ctas_per_sm[fma];
     cudaError_t e = cudaMemsetAsync(p.next, 0, sizeof(unsigned long long), stream);
     UME_REQUIRE(e == cudaSuccess, UME_ERR_CUDA, "moments_warp: cudaMemsetAsync: %s", cudaGetErrorString(e));
+#endif
     kern<<<(unsigned)grid, 32 * kWarps, 0, stream>>>(p);
     count_launch();
     return check_launch("moments_warp_kernel");
+}
+
+template <int MODE>
+int launch_c(const Params& p, int C, bool fma, cudaStream_t stream) {
+    switch (C) {
+        case 16: return launch<4, MODE>(p, fma, stream);
+        case 32: return launch<8, MODE>(p, fma, stream);
+        case 64: return launch<16, MODE>(p, fma, stream);
+        default: return launch<32, MODE>(p, fma, stream);
+    }
 }
 
 }  // namespace warpk
