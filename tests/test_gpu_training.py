@@ -97,8 +97,8 @@ def test_ume_losses_against_reference_golden(ume, golden):
     ume_loss, kp_v, kp_r, U_v, U_r, ratio, valid = ume_fn(dev(g["velo_pts"]), dev(g["velo_seg"]), vf, dev(g["ref_pts"]), rf, gt)
     reg_loss, rre, rte = reg_fn(dev(g["velo_pts"]), U_v, dev(g["ref_pts"]), U_r, gt, ratio, valid)
     assert close(host(U_v), g["loss_ume_velo"], 2e-5) and close(host(U_r), g["loss_ume_ref"], 2e-5)
-    assert abs(float(ume_loss) - float(g["ume_loss"])) < 2e-3 * abs(float(g["ume_loss"])) + 1e-6
-    assert abs(float(reg_loss) - float(g["reg_loss"])) < 2e-3 * abs(float(g["reg_loss"]))
+    assert abs(float(ume_loss.detach()) - float(g["ume_loss"])) < 2e-3 * abs(float(g["ume_loss"])) + 1e-6
+    assert abs(float(reg_loss.detach()) - float(g["reg_loss"])) < 2e-3 * abs(float(g["reg_loss"]))
     assert np.abs(host(rte) - g["loss_rte"]).max() < 2e-3 * np.abs(g["loss_rte"]).max()
     (ume_loss + reg_loss).backward()
     assert close(host(vf.grad), g["loss_grad_velo_feat"], 5e-3)

@@ -6,7 +6,8 @@ descriptor-and-registration hot path, behind the reference's own Python call sig
 
 See DESIGN.md for the path and its boundary, include/umereg_b200.h for the C ABI.
 """
-from .api import (ball_query, knn_points, knn_gather, knn1_transfer, ume_moments, my_ume_generation,
+from .api import (ball_query, knn_points, knn_gather, knn1_transfer, ume_moments, ume_moments_backward,
+                  neighbor_count, my_ume_generation,
                   create_local_ume_matrix, ume_descriptors, descriptor_cdist, ume_cdist, rigid_solve,
                   batch_estimate_transform_ume_old, relative_rotation_error, ball_query_gather, ume_kp_layer,
                   register_hypotheses, feature_spatial_var, cauchy_kernel, correlation_scores,
@@ -14,7 +15,8 @@ from .api import (ball_query, knn_points, knn_gather, knn1_transfer, ume_moments
                   select_hypothesis, config)
 from .patch import patch_reference
 
-__all__ = ["ball_query", "knn_points", "knn_gather", "knn1_transfer", "ume_moments", "my_ume_generation",
+__all__ = ["ball_query", "knn_points", "knn_gather", "knn1_transfer", "ume_moments", "ume_moments_backward",
+           "neighbor_count", "my_ume_generation",
            "create_local_ume_matrix", "ume_descriptors", "descriptor_cdist", "ume_cdist", "rigid_solve",
            "batch_estimate_transform_ume_old", "relative_rotation_error", "ball_query_gather", "ume_kp_layer",
            "register_hypotheses", "feature_spatial_var", "cauchy_kernel", "correlation_scores",
