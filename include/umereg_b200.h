@@ -47,7 +47,9 @@ typedef enum ume_status {
                                       evaluate.py:59 (training path: utils/loc_utils.py:157-161 with
                                       normalized_ume=False, and the differentiable wrapper)          */
 #define UME_FLAG_CTA_MOMENTS   4u  /* ume_moments_f32: force the CTA-per-keypoint kernel (the default
-                                      for C in {16,32,64,128} is the warp-per-keypoint kernel)      */
+                                      for C in {16,32,64,128} and B*n >= 3072 keypoints is the
+                                      warp-per-keypoint kernel)                                      */
+#define UME_FLAG_WARP_MOMENTS  16u /* ume_moments_f32: warp-per-keypoint kernel also for small launches */
 
 int ume_abi_version(void);
 const char* ume_last_error(void);

@@ -19,16 +19,16 @@ def ume():
     from umeregrobust_b200 import _lib
     _lib.lib()                                   # fails loudly when the CUDA library is missing
     yield u
-    u.config.update(fma_dist=False, cell_div2=False, cdist_impl=None, cta_moments=False)
+    u.config.update(fma_dist=False, cell_div2=False, cdist_impl=None, cta_moments=False, warp_moments=False)
 
 
 @pytest.fixture(params=["warp", "cta"])
 def moment_kernel(request, ume):
     """Both gather+moment kernels: one warp per keypoint (default for C in {16,32,64,128}) and one CTA
     per keypoint (every other channel count, or forced with config['cta_moments'])."""
-    ume.config.update(cta_moments=(request.param == "cta"))
+    ume.config.update(cta_moments=(request.param == "cta"), warp_moments=(request.param == "warp"))
     yield request.param
-    ume.config.update(cta_moments=False)
+    ume.config.update(cta_moments=False, warp_moments=False)
 
 
 def dev(x):

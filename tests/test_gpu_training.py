@@ -53,10 +53,14 @@ def test_moments_backward_matches_oracle(ume, C, K):
     F = training.ume_moments_autograd(dev(pts), dev(kp), feat, K, 4.0, normalized=False)
     (F * dev(gF)).sum().backward()
     assert close(host(feat.grad), ref, 2e-5)
+    # raw vs normalised output of the forward kernel (two launches, two summation orders): compared
+    # where the normaliser sum_c F0 is well conditioned (random features make it nearly cancel elsewhere)
     Fn = host(ume.ume_moments(dev(pts), dev(kp), feat.detach(), K, 4.0))
     Fr = host(F)
-    # (two launches, two summation orders; the normaliser sum_c F0 of random features is ill-conditioned)
-    assert close(Fr / (Fr[..., :1].sum(-2, keepdims=True) + 1e-6), Fn, 5e-4)
+    den = Fr[..., :1].sum(-2, keepdims=True)
+    ok = (np.abs(den) > 0.25 * np.abs(Fr[..., :1]).sum(-2, keepdims=True))[..., 0, 0]
+    assert ok.sum() > 10
+    assert close((Fr / (den + 1e-6))[ok], Fn[ok], 1e-4)
 
 
 def test_generate_ume_from_keypoints2_against_reference_golden(ume, golden):

@@ -21,6 +21,7 @@ UME_FLAG_FMA_DIST = 1
 UME_FLAG_CELL_DIV2 = 2
 UME_FLAG_CTA_MOMENTS = 4
 UME_FLAG_RAW_MOMENTS = 8
+UME_FLAG_WARP_MOMENTS = 16
 
 _lock = threading.Lock()
 _lib = None

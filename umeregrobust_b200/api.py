@@ -19,16 +19,19 @@ _KNN = collections.namedtuple("_KNN", ["dists", "idx", "knn"])
 #   fma_dist : evaluate the squared distance with fused multiply-adds (what nvcc makes of
 #              pytorch3d's CUDA kernel) instead of separately rounded mul/add (pytorch3d CPU build)
 #   cell_div2: search grid with cell = radius / 2
+#   cta_moments / warp_moments: force the CTA-per-keypoint / warp-per-keypoint gather+moment kernel
+#              (default: warp kernel for C in {16,32,64,128} and launches of >= 3072 keypoints)
 #   cdist_impl: 0 = fp32 SIMT distance kernel, 1 = tcgen05 tensor-core kernel
 #               (C = 32 / 64 only), None = tensor cores whenever the channel count allows
-config = {"fma_dist": False, "cell_div2": False, "cdist_impl": None, "cta_moments": False}
+config = {"fma_dist": False, "cell_div2": False, "cdist_impl": None, "cta_moments": False, "warp_moments": False}
 
 _workspaces = {}
 
 
 def _flags():
     return ((_lib.UME_FLAG_FMA_DIST if config["fma_dist"] else 0) | (_lib.UME_FLAG_CELL_DIV2 if config["cell_div2"] else 0)
-            | (_lib.UME_FLAG_CTA_MOMENTS if config["cta_moments"] else 0))
+            | (_lib.UME_FLAG_CTA_MOMENTS if config["cta_moments"] is True else 0)
+            | (_lib.UME_FLAG_WARP_MOMENTS if config["cta_moments"] is False and config.get("warp_moments") else 0))
 
 
 def _stream():

@@ -246,6 +246,8 @@ int launch_moments(const MomentsParams& p, int B, bool fma, cudaStream_t stream)
 
 }  // namespace
 
+static constexpr long long kWarpKernelMinKeypoints = 3072;
+
 static int moments_cap(int C, int K) {
     (void)K;
     int cap = 2048;
@@ -288,7 +290,10 @@ extern "C" int ume_moments_f32(const float* pts, const float* kpts, const float*
     const bool warp_ok = aligned && (C == 16 || C == 32 || C == 64 || C == 128);
     const bool raw = (flags & UME_FLAG_RAW_MOMENTS) != 0;
     UME_REQUIRE(!raw || warp_ok, UME_ERR_UNSUPPORTED, "ume_moments_f32: raw moments need C in {16,32,64,128} (C = %d)", C);
-    if ((!(flags & UME_FLAG_CTA_MOMENTS) || raw) && warp_ok) {
+    // A warp takes ~80 us per keypoint (latency-bound, hidden by the 32 x 148 warps in flight); a 256-thread
+    // CTA takes ~16 us.  Launches too small to fill the warp slots are faster on the CTA kernel.
+    const bool small = (long long)B * n < kWarpKernelMinKeypoints;
+    if ((!((flags & UME_FLAG_CTA_MOMENTS) || (small && !(flags & UME_FLAG_WARP_MOMENTS))) || raw) && warp_ok) {
         // one warp per keypoint (moments_warp.cuh): the default for the channel counts it is built for
         warpk::Params wp;
         wp.grid = p.grid; wp.kpts = kpts; wp.feat = feat; wp.F = F; wp.Fc = Fc; wp.count = count;
