@@ -238,9 +238,16 @@ struct CorrParams {
     float inv_sigma;
 };
 
+#ifndef UME_CORR_MINB
+#define UME_CORR_MINB 6            // CTAs per SM the register allocation is capped for
+#endif
+
 template <int C4, typename Top, bool kFma>
-__global__ void __launch_bounds__(kCorrThreads) corr_score_kernel(CorrParams p) {
+__global__ void __launch_bounds__(kCorrThreads, UME_CORR_MINB) corr_score_kernel(CorrParams p) {
     __shared__ float s_red[kCorrThreads / 32];
+    // the thread's source feature row lives in shared memory ([chunk][thread]: conflict-free 16-byte
+    // reads), not in 4*C4 registers: the K-best list already takes 2K of them
+    __shared__ float4 s_sf[C4][kCorrThreads];
     const GridHeader hs = p.src_grid.hdr[0];
     const GridHeader ht = p.tgt_grid.hdr[0];
     const int* cs = p.tgt_grid.cell_start;
@@ -248,14 +255,11 @@ __global__ void __launch_bounds__(kCorrThreads) corr_score_kernel(CorrParams p) 
     const int t = blockIdx.x * kCorrThreads + threadIdx.x;
     const bool active = t < hs.n_sorted;
     float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 sf[C4];
-#pragma unroll
-    for (int c = 0; c < C4; ++c) sf[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) {
         me = p.src_grid.sorted[t];
         const float* row = p.wf_src + (size_t)__float_as_int(me.w) * (C4 * 4);
 #pragma unroll
-        for (int c = 0; c < C4; ++c) sf[c] = ldg_f4(row + 4 * c);
+        for (int c = 0; c < C4; ++c) s_sf[c][threadIdx.x] = ldg_f4(row + 4 * c);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int hyp = blockIdx.y; hyp < p.n_hyp; hyp += gridDim.y) {
@@ -275,7 +279,8 @@ __global__ void __launch_bounds__(kCorrThreads) corr_score_kernel(CorrParams p) 
 #pragma unroll
                 for (int c = 0; c < C4; ++c) {
                     const float4 g = ldg_f4(row + 4 * c);
-                    v = fmaf(sf[c].x, g.x, v); v = fmaf(sf[c].y, g.y, v); v = fmaf(sf[c].z, g.z, v); v = fmaf(sf[c].w, g.w, v);
+                    const float4 a = s_sf[c][threadIdx.x];
+                    v = fmaf(a.x, g.x, v); v = fmaf(a.y, g.y, v); v = fmaf(a.z, g.z, v); v = fmaf(a.w, g.w, v);
                 }
                 const float e = sqrtf(dk) * p.inv_sigma;             // |p - q| / sigma
                 acc = fmaf(v, 1.f / fmaf(e, e, 1.f), acc);            // cauchy_kernel (:588-589)
