@@ -93,12 +93,19 @@ __global__ void grid_params_kernel(const int* __restrict__ bbox, GridHeader* __r
     }
     if (!(s > emax * 1e-6f)) s = emax;          // absurdly small cell: a single cell
     if (!(s > 0.f)) s = 1.f;
+    // Radius-query grids (cell and expand given) over a slab-like domain — the queries' z range is at
+    // most 2 r, the LiDAR case — get ONE layer of cells in z: the table shrinks to nx*ny cells (a
+    // finer xy grid fits), a query touches a handful of cell rows instead of rows x layers, and the
+    // exact distance test sorts out z anyway.  (cell_coord clamps z to layer 0; neighbors.cuh treats
+    // the outermost layers as unbounded.)  The k-NN grids keep cubic cells: their ring bounds need them.
+    const bool flat = (cell > 0.f) && (r > 0.f) && (ext[2] <= 4.1f * r);
     int n[3];
     for (int it = 0; it < 256; ++it) {
         double prod = 1.0;
         for (int d = 0; d < 3; ++d) {
             float c = floorf(ext[d] / s) + 1.f;
             n[d] = (c < 1.f) ? 1 : (c > 1.0e6f ? 1000000 : (int)c);
+            if (d == 2 && flat) n[d] = 1;
             prod *= (double)n[d];
         }
         if (prod <= (double)cells_cap) break;

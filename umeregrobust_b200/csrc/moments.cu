@@ -247,6 +247,9 @@ int launch_moments(const MomentsParams& p, int B, bool fma, cudaStream_t stream)
 }  // namespace
 
 static constexpr long long kWarpKernelMinKeypoints = 3072;
+#ifndef UME_WARPK_CELL_DIV
+#define UME_WARPK_CELL_DIV 2       // search-grid cell = radius / this for the warp-per-keypoint kernel
+#endif
 
 static int moments_cap(int C, int K) {
     (void)K;
@@ -281,11 +284,6 @@ extern "C" int ume_moments_f32(const float* pts, const float* kpts, const float*
                 ume_moments_workspace_bytes(B, N, n, C, K), ws_bytes);
     Workspace w(ws, ws_bytes);
     MomentsParams p;
-    int rc = grid_build(pts, kpts, B, N, n, fabsf(radius), fabsf(radius) / ((flags & UME_FLAG_CELL_DIV2) ? 2.f : 1.f), kCellsCap, w, &p.grid, stream);
-    if (rc != UME_OK) return rc;
-    p.kpts = kpts; p.feat = feat; p.F = F; p.Fc = Fc; p.count = count;
-    p.n = n; p.C = C; p.K = K; p.cap = moments_cap(C, K); p.radius = radius;
-    const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
     const bool aligned = reinterpret_cast<uintptr_t>(feat) % 16 == 0;
     const bool warp_ok = aligned && (C == 16 || C == 32 || C == 64 || C == 128);
     const bool raw = (flags & UME_FLAG_RAW_MOMENTS) != 0;
@@ -293,7 +291,15 @@ extern "C" int ume_moments_f32(const float* pts, const float* kpts, const float*
     // A warp takes ~80 us per keypoint (latency-bound, hidden by the 32 x 148 warps in flight); a 256-thread
     // CTA takes ~16 us.  Launches too small to fill the warp slots are faster on the CTA kernel.
     const bool small = (long long)B * n < kWarpKernelMinKeypoints;
-    if ((!((flags & UME_FLAG_CTA_MOMENTS) || (small && !(flags & UME_FLAG_WARP_MOMENTS))) || raw) && warp_ok) {
+    const bool use_warp = (!((flags & UME_FLAG_CTA_MOMENTS) || (small && !(flags & UME_FLAG_WARP_MOMENTS))) || raw) && warp_ok;
+    // cells of radius/2 for the warp kernel (its two candidate scans pay for every candidate twice)
+    const float cell = fabsf(radius) / (use_warp ? (float)UME_WARPK_CELL_DIV : ((flags & UME_FLAG_CELL_DIV2) ? 2.f : 1.f));
+    int rc = grid_build(pts, kpts, B, N, n, fabsf(radius), cell, kCellsCap, w, &p.grid, stream);
+    if (rc != UME_OK) return rc;
+    p.kpts = kpts; p.feat = feat; p.F = F; p.Fc = Fc; p.count = count;
+    p.n = n; p.C = C; p.K = K; p.cap = moments_cap(C, K); p.radius = radius;
+    const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
+    if (use_warp) {
         // one warp per keypoint (moments_warp.cuh): the default for the channel counts it is built for
         warpk::Params wp;
         wp.grid = p.grid; wp.kpts = kpts; wp.feat = feat; wp.F = F; wp.Fc = Fc; wp.count = count;
@@ -336,7 +342,7 @@ static int moments_aux(const float* pts, const float* kpts, const float* gF, int
     UME_REQUIRE(ws && ws_bytes >= ume_moments_workspace_bytes(B, N, n, C, K), UME_ERR_WORKSPACE, "%s: workspace too small", who);
     Workspace w(ws, ws_bytes);
     warpk::Params wp;
-    int rc = grid_build(pts, kpts, B, N, n, fabsf(radius), fabsf(radius) / ((flags & UME_FLAG_CELL_DIV2) ? 2.f : 1.f), kCellsCap, w, &wp.grid, stream);
+    int rc = grid_build(pts, kpts, B, N, n, fabsf(radius), fabsf(radius) / (float)UME_WARPK_CELL_DIV, kCellsCap, w, &wp.grid, stream);
     if (rc != UME_OK) return rc;
     wp.kpts = kpts; wp.feat = nullptr; wp.F = nullptr; wp.Fc = nullptr; wp.count = count;
     wp.gF = gF; wp.grad_feat = grad_feat; wp.raw = 1;

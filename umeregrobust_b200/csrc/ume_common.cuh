@@ -123,7 +123,10 @@ int grid_build(const float* pts, const float* q, int B, int N, int nq, float exp
 
 // Cells per cloud.  8192 keeps the binning kernel's shared-memory histogram at 32 KB (4 CTAs per SM)
 // and the cell table L1/L2-friendly; a KITTI-shape cloud at cell = radius needs ~4.6 k cells.
-static constexpr int kCellsCap = 8192;
+#ifndef UME_CELLS_CAP
+#define UME_CELLS_CAP 8192
+#endif
+static constexpr int kCellsCap = UME_CELLS_CAP;
 static constexpr int kMaxPoints = 2097152;
 
 }  // namespace ume
