@@ -96,6 +96,22 @@ def test_ball_query_edge_cases(ume):
         ume.ball_query(dev(p2), dev(np.zeros((2, 5, 3), np.float32)), K=2, radius=1.0)  # batch mismatch
 
 
+def test_ball_query_lengths(ume):
+    # pytorch3d's heterogeneous batches (utils/loc_utils.py:113 passes lengths1): queries past
+    # lengths1[b] get the padding values, cloud rows past lengths2[b] are never neighbours
+    pts, rng = cloud(9, 3, 3000)
+    q = pts[:, rng.choice(3000, 200, replace=False)].copy()
+    l1, l2 = np.array([200, 57, 0]), np.array([3000, 1234, 10])
+    out = ume.ball_query(dev(q), dev(pts), lengths1=dev(l1), lengths2=dev(l2), K=64, radius=2.5)
+    for b in range(3):
+        ref = p3d.ball_query_c(q[b:b + 1, :l1[b]], pts[b:b + 1, :l2[b]], 64, 2.5)
+        assert np.array_equal(host(out.idx)[b, :l1[b]], ref.idx[0])
+        assert np.array_equal(host(out.dists)[b, :l1[b]], ref.dists[0])
+        assert np.array_equal(host(out.knn)[b, :l1[b]], ref.knn[0])
+        assert (host(out.idx)[b, l1[b]:] == -1).all() and (host(out.dists)[b, l1[b]:] == 0).all()
+        assert (host(out.knn)[b, l1[b]:] == 0).all()
+
+
 # ----------------------------------------------------------------------------- moments
 @pytest.mark.parametrize("C", [4, 8, 16, 32, 64, 128, 12, 33, 200])
 def test_moments_all_channel_counts(ume, moment_kernel, C):

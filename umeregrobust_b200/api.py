@@ -81,11 +81,15 @@ def _dev_f32(t, name, ndim=None):
 def ball_query(p1, p2, lengths1=None, lengths2=None, K=500, radius=0.2, return_nn=True):
     """pytorch3d.ops.ball_query as called at evaluate.py:51 and utils/loc_utils.py:383-384:
     first K rows of p2 (row order) with dist^2 < radius^2; idx -1 padded (int64), dists 0 padded,
-    knn zero padded.  Returns a namedtuple (dists, idx, knn)."""
-    if lengths1 is not None or lengths2 is not None:
-        raise NotImplementedError("ball_query: heterogeneous lengths are not used by the reference and not supported")
+    knn zero padded.  Returns a namedtuple (dists, idx, knn).
+    lengths1 / lengths2 (B,) (utils/loc_utils.py:113 passes lengths1): rows of p1 past lengths1[b] get
+    the padding values, rows of p2 past lengths2[b] are never neighbours (they are handed to the
+    kernel as NaN points, which the search grid drops)."""
     p1 = _dev_f32(p1, "p1", 3)
     p2 = _dev_f32(p2, "p2", 3)
+    if lengths2 is not None:
+        beyond = torch.arange(p2.shape[1], device=p2.device)[None] >= torch.as_tensor(lengths2, device=p2.device)[:, None]
+        p2 = torch.where(beyond[..., None], torch.full_like(p2, float("nan")), p2)
     if p1.shape[0] != p2.shape[0] or p1.shape[2] != 3 or p2.shape[2] != 3:
         raise ValueError("ball_query: p1 %s and p2 %s must be (B,P,3) with equal B" % (tuple(p1.shape), tuple(p2.shape)))
     B, P1, _ = p1.shape
@@ -101,6 +105,12 @@ def ball_query(p1, p2, lengths1=None, lengths2=None, K=500, radius=0.2, return_n
         rc = L.ume_ball_query_f32(_ptr(p1), _ptr(p2), B, P1, P2, K, float(radius), _flags(), _ptr(idx), _ptr(dists),
                                   _ptr(nn), None, _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "ball_query")
+    if lengths1 is not None:
+        beyond = torch.arange(P1, device=p1.device)[None] >= torch.as_tensor(lengths1, device=p1.device)[:, None]
+        idx[beyond] = -1
+        dists[beyond] = 0
+        if nn is not None:
+            nn[beyond] = 0
     return _BallQuery(dists, idx, nn)
 
 
