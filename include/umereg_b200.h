@@ -198,6 +198,15 @@ size_t ume_voxel_unique_workspace_bytes(int N);
 int ume_voxel_unique_f32(const float* pts, int N, float voxel, int64_t* index, int32_t* coords, int32_t* count,
                          void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- optimal matching (host)
+ * Replaces scipy.optimize.linear_sum_assignment at evaluate.py:216-222 (hungarian_matching_flag, off in
+ * every shipped config), which the reference also runs on the host over `D[b].cpu().numpy()`.
+ * HOST pointers (the only `_host` entry point): cost (n_rows, n_cols) row-major float32, finite or
+ * +inf; outputs min(n_rows, n_cols) pairs with row_ind ascending — scipy's output convention.
+ * Shortest augmenting paths in double precision: the minimum-cost assignment. */
+int ume_linear_sum_assignment_host_f32(const float* cost_host, int n_rows, int n_cols, int64_t* row_ind_host,
+                                       int64_t* col_ind_host);
+
 /* ---------------------------------------------------------------- stage profiler
  * When enabled, every stage brackets its kernel launches with CUDA events on the launching
  * stream; ume_profile_read() synchronises those events and returns the accumulated device time

@@ -451,3 +451,25 @@ def test_cdist_tcgen05_matches_fp64_and_simt(ume, C, B, n1, n2):
     # arg-min only (no D written)
     _, am2, dm2 = ume.descriptor_cdist(Q1, Q2, want_D=False, want_argmin=True, impl=1)
     assert np.array_equal(host(am2), host(am1)) and np.array_equal(host(dm2), host(dm1))
+
+
+def test_register_hypotheses_hungarian_option(ume):
+    # evaluate.py:216-222: one-to-one matches from the assignment solver on the device-computed D;
+    # hypotheses solved for exactly those pairs
+    scipy_opt = pytest.importorskip("scipy.optimize")
+    p = synth.make_pair(21, N=6000, C=32, n_kp=96, generator="disc", exact_copy=True)
+    d = {k: dev(v[None]) for k, v in p.items() if k.endswith(("pts", "feat", "kp"))}
+    args = (d["src_pts"], d["src_feat"], d["src_kp"], d["tgt_pts"], d["tgt_feat"], d["tgt_kp"], 750, 5.0)
+    out = ume.register_hypotheses(*args, matching="hungarian")
+    r, c = scipy_opt.linear_sum_assignment(host(out["D"])[0])
+    m = host(out["match"])[0]
+    assert np.array_equal(m[:, 0], r) and np.array_equal(m[:, 1], c)
+    assert sorted(m[:, 1].tolist()) == list(range(96))                           # one-to-one
+    assert np.array_equal(host(out["dmin"])[0], host(out["D"])[0][r, c])
+    ref = ume.register_hypotheses(*args)                                          # arg-min path, same moments
+    T = host(ume.rigid_solve(ref["F_src"], ref["F_tgt"], dev(m[None, :, 0]), dev(m[None, :, 1])))
+    same = m[:, 1] == host(ref["match"])[0, :, 1]
+    assert same.mean() > 0.5
+    ang = orc.rotation_angle_rad(host(out["T"])[0][same][:, :3, :3].astype(np.float64), host(ref["T"])[0][same][:, :3, :3].astype(np.float64))
+    assert np.max(ang) < 1e-5
+    assert T.shape == (1, 96, 4, 4)

@@ -12,7 +12,7 @@ from .api import (ball_query, knn_points, knn_gather, knn1_transfer, ume_moments
                   batch_estimate_transform_ume_old, relative_rotation_error, ball_query_gather, ume_kp_layer,
                   register_hypotheses, feature_spatial_var, cauchy_kernel, correlation_scores,
                   pc_corr_cost_pytorch3d, weighted_features, FeatureCorrelator, weighted_match_subsample, sparse_quantize,
-                  select_hypothesis, config)
+                  select_hypothesis, linear_sum_assignment, hungarian_match, config)
 from .patch import patch_reference
 
 __all__ = ["ball_query", "knn_points", "knn_gather", "knn1_transfer", "ume_moments", "ume_moments_backward",
@@ -21,5 +21,5 @@ __all__ = ["ball_query", "knn_points", "knn_gather", "knn1_transfer", "ume_momen
            "batch_estimate_transform_ume_old", "relative_rotation_error", "ball_query_gather", "ume_kp_layer",
            "register_hypotheses", "feature_spatial_var", "cauchy_kernel", "correlation_scores",
            "pc_corr_cost_pytorch3d", "weighted_features", "FeatureCorrelator", "weighted_match_subsample",
-           "sparse_quantize", "select_hypothesis",
+           "sparse_quantize", "select_hypothesis", "linear_sum_assignment", "hungarian_match",
            "patch_reference", "config"]

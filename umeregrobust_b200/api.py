@@ -605,6 +605,35 @@ def select_hypothesis(src_pts_raw, tgt_pts_raw, src_pts, tgt_pts, src_feat, tgt_
     return hypotheses[best], best, score
 
 
+# ----------------------------------------------------------------------------- Hungarian option (f4)
+def linear_sum_assignment(cost):
+    """scipy.optimize.linear_sum_assignment for one (n1,n2) float32 cost matrix on the HOST (a CPU
+    tensor or numpy array), as evaluate.py:219 calls it: (row_ind, col_ind) int64 numpy arrays,
+    row_ind ascending."""
+    import numpy as np
+    c = np.ascontiguousarray(cost.detach().cpu().numpy() if torch.is_tensor(cost) else cost, dtype=np.float32)
+    if c.ndim != 2:
+        raise ValueError("linear_sum_assignment: expected a matrix")
+    k = min(c.shape)
+    rows, cols = np.empty(k, np.int64), np.empty(k, np.int64)
+    rc = _lib.lib().ume_linear_sum_assignment_host_f32(c.ctypes.data, c.shape[0], c.shape[1], rows.ctypes.data, cols.ctypes.data)
+    _lib.check(rc, "linear_sum_assignment")
+    return rows, cols
+
+
+def hungarian_match(D):
+    """evaluate.py:216-222 (`hungarian_matching_flag`): one-to-one matches minimising the summed
+    distance.  D (B,n1,n2) on the device -> m (B, min(n1,n2), 2) int64 on the device.  Like the
+    reference, the assignment itself is solved on the host from a copy of D (one D2H per call)."""
+    Dh = D.detach().float().cpu()
+    out = torch.empty((D.shape[0], min(D.shape[1], D.shape[2]), 2), dtype=torch.int64)
+    for b in range(D.shape[0]):
+        r, c = linear_sum_assignment(Dh[b])
+        out[b, :, 0] = torch.from_numpy(r)
+        out[b, :, 1] = torch.from_numpy(c)
+    return out.to(D.device)
+
+
 # ----------------------------------------------------------------------------- match sub-sampling (f2)
 def weighted_match_subsample(ume_d, tau, num_samples, generator=None):
     """Device-side equivalent of evaluate.py:233-245: draw `num_samples` of the n matches WITHOUT
@@ -626,7 +655,7 @@ def weighted_match_subsample(ume_d, tau, num_samples, generator=None):
 
 # ----------------------------------------------------------------------------- fused hot path
 def register_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K, radius, want_D=False,
-                        centered=True, buf=None):
+                        centered=True, buf=None, matching="argmin"):
     """evaluate.py:206-257 for a whole batch, without the host-RNG sub-sampling (:233-245): UME
     matrices for both clouds, subspace distances with fused arg-min, one rigid hypothesis per
     source keypoint from its best-matching target keypoint.
@@ -636,6 +665,8 @@ def register_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K,
     fp32); centered=False follows the reference's absolute-coordinate arithmetic.
     `buf`: an arena dict; when given, every output lives in it and is REUSED by the next call with
     the same shapes (the returned tensors are then only valid until that next call).
+    matching="hungarian" (evaluate.py:216-222, `hungarian_matching_flag`): one-to-one matches from the
+    host assignment solver instead of the row arg-min (one D2H copy of D per call, like the reference).
     Returns dict(F_src, F_tgt, match (B,n,2) int64, dmin (B,n), T (B,n,4,4), D or None)."""
     if centered:
         F_src, Fc_src = ume_moments(src_pts, src_kp, src_feat, K, radius, return_centered=True, buf=buf, tag="_src")
@@ -645,8 +676,16 @@ def register_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K,
         F_src = ume_moments(src_pts, src_kp, src_feat, K, radius, buf=buf, tag="_src")
         F_tgt = ume_moments(tgt_pts, tgt_kp, tgt_feat, K, radius, buf=buf, tag="_tgt")
         A, Bm = F_src, F_tgt
+    if matching not in ("argmin", "hungarian"):
+        raise ValueError("register_hypotheses: matching must be 'argmin' or 'hungarian'")
     D, am, dm = descriptor_cdist(ume_descriptors(A, buf=buf, tag="_src"), ume_descriptors(Bm, buf=buf, tag="_tgt"),
-                                 want_D=want_D, want_argmin=True, buf=buf)
+                                 want_D=want_D or matching == "hungarian", want_argmin=True, buf=buf)
+    if matching == "hungarian":
+        m = hungarian_match(D)
+        gi, hi = m[..., 0].contiguous(), m[..., 1].contiguous()
+        T = rigid_solve(A, Bm, gi, hi, src_kp if centered else None, tgt_kp if centered else None, buf=buf)
+        dsel = torch.gather(torch.gather(D, 1, gi[..., None].expand(-1, -1, D.shape[2])), 2, hi[..., None])[..., 0]
+        return dict(F_src=F_src, F_tgt=F_tgt, match=m, dmin=dsel, T=T, D=D)
     if centered:
         T = rigid_solve(A, Bm, None, am, src_kp, tgt_kp, buf=buf)
     else:
