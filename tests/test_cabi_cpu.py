@@ -93,3 +93,53 @@ def test_patch_reference_rebinds_names():
     assert fake_eval.my_ume_generation is ume.my_ume_generation
     assert fake_loc.ume_cdist is ume.ume_cdist and fake_eval.ball_query is ume.ball_query
     assert ("evaluate", "my_ume_generation") in done and len(done) == 13
+
+
+def test_new_entry_points_validate_without_a_device(handle):
+    null = ctypes.c_void_p(None)
+    one = ctypes.c_void_p(256)
+    # backward: C outside the warp kernel's channel counts
+    rc = handle.ume_moments_backward_f32(one, one, one, 1, 10, 2, 12, 5, 1.0, 0, one, one, 1 << 30, null)
+    assert rc == -3 and b"C = 12" in handle.ume_last_error()
+    rc = handle.ume_moments_backward_f32(one, one, null, 1, 10, 2, 32, 5, 1.0, 0, one, one, 1 << 30, null)
+    assert rc == -1
+    rc = handle.ume_neighbor_count_f32(one, one, 1, 10, 2, 5, 1.0, 0, null, one, 1 << 30, null)
+    assert rc == -1
+    rc = handle.ume_neighbor_count_f32(one, one, 1, 10, 2, 5, 1.0, 0, one, one, 16, null)
+    assert rc == -2
+    # raw moments need the warp kernel's channel counts
+    rc = handle.ume_moments_f32(one, one, one, 1, 10, 2, 12, 5, 1.0, _lib.UME_FLAG_RAW_MOMENTS, one, null, null, one, 1 << 30, null)
+    assert rc == -3
+    rc = handle.ume_voxel_unique_f32(one, 10, 0.0, one, null, one, one, 1 << 30, null)
+    assert rc == -1 and b"voxel size" in handle.ume_last_error()
+    assert handle.ume_voxel_unique_workspace_bytes(0) == 0 and handle.ume_voxel_unique_workspace_bytes(1000) >= 2048 * 12
+
+
+def test_training_helpers_on_cpu():
+    # host-side logic of the training mirror that needs no device: the "selected rows in descending
+    # order, zero padded" idiom of utils/loc_utils.py:104-111
+    torch = pytest.importorskip("torch")
+    from umeregrobust_b200 import training
+    cond = torch.tensor([[True, False, True, True, False], [False, False, False, True, False]])
+    idx, n = training._descending(cond)
+    assert idx.tolist() == [[3, 2, 0, 0, 0], [3, 0, 0, 0, 0]] and n.tolist() == [3, 1]
+    # the reference idiom, literally
+    mask = -1 * torch.ones_like(cond, dtype=torch.long)
+    w = torch.where(cond)
+    mask[w] = w[1]
+    mask = mask.sort(dim=1, descending=True)[0]
+    lengths = (mask > -1).sum(dim=-1)
+    mask[mask == -1] = 0
+    assert torch.equal(mask, idx) and torch.equal(lengths, n)
+    # differentiable rigid solve recovers a known transform from exact UME pairs (CPU torch, fp64)
+    g = torch.Generator().manual_seed(0)
+    pts = torch.randn(200, 3, generator=g, dtype=torch.float64) * 3
+    f = torch.rand(200, 8, generator=g, dtype=torch.float64)
+    A = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64)).Q
+    R = A * torch.sign(torch.det(A))
+    t = torch.tensor([1.0, -2.0, 0.5], dtype=torch.float64)
+    q = pts @ R.T + t
+    G = torch.cat([f.sum(0)[:, None], f.T @ pts], dim=1)[None]
+    H = torch.cat([f.sum(0)[:, None], f.T @ q], dim=1)[None]
+    T = training.rigid_from_ume_autograd(G, H)[0]
+    assert torch.allclose(T[:3, :3], R, atol=1e-9) and torch.allclose(T[:3, 3], t, atol=1e-8)
