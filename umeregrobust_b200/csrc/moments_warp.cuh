@@ -21,6 +21,10 @@
 #pragma once
 #include "neighbors.cuh"
 
+// the kernel is one body for three modes: code after a mode's early exit is unreachable in that
+// instantiation only
+#pragma nv_diag_suppress code_is_unreachable
+
 namespace ume {
 namespace warpk {
 
