@@ -289,7 +289,7 @@ def run_b200(args, wl):
                      "launches_timed": mom_n, "peak_source": peaks_note + " (MEASURED_PEAKS.json hbm_gbs)"},
         "stages": stages,
     }
-    if not args.no_cpu_baseline and world >= 1:
+    if not args.no_cpu_baseline and world == 1:          # the contract: rank 0 at N = 1 only
         threads = os.cpu_count() or 1
         from oracle import pytorch3d_ops as p3d
         n_cpu = max(1, min(args.cpu_baseline_pairs, pairs))
