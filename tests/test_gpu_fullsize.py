@@ -159,3 +159,23 @@ def test_cuda_graph_replay_matches_eager(ume):
     eager = eng_eager = RegistrationEngine(K=K_NN, radius=RADIUS, want_D=True).register(d)
     torch.cuda.synchronize()
     assert np.array_equal(host(out2["match"]), host(eager["match"]))
+
+
+def test_moments_backward_is_adjoint_at_full_size(ume):
+    # size-independent property at the benchmark size (120 000 points, 1024 keypoints, K = 750): the
+    # raw moment build is linear in the features and the scatter backward is its transpose, so
+    # <F_raw(feat), w> == <feat, backward(w)> for any feat, w (fp32 sums: 1e-4 relative)
+    p = synth.make_pair(3, N=120000, C=32, n_kp=1024, generator="disc")
+    rng = np.random.default_rng(0)
+    pts, kp, feat = dev(p["src_pts"][None]), dev(p["src_kp"][None]), dev(p["src_feat"][None])
+    w = dev(rng.normal(size=(1, 1024, 32, 4)).astype(np.float32))
+    ume.config["warp_moments"] = True
+    try:
+        F = ume.ume_moments(pts, kp, feat, K_NN, RADIUS, raw=True)
+        g = ume.ume_moments_backward(pts, kp, w, K_NN, RADIUS)
+    finally:
+        ume.config["warp_moments"] = False
+    lhs = float((F.double() * w.double()).sum())
+    rhs = float((feat.double() * g.double()).sum())
+    scale = float((F.double().abs() * w.double().abs()).sum())
+    assert abs(lhs - rhs) < 1e-5 * scale, (lhs, rhs, scale)
