@@ -143,6 +143,24 @@ int ume_rigid_solve_f32(const float* G, const float* H, const int64_t* gi, const
                         const float* offG, const float* offH, int B, int nG, int nH, int nm, int C,
                         float* T, void* stream);
 
+/* Replaces utils/eval_utils.py:60-76 `relative_rotation_error(R, R_hat)`:
+ *   out[i] = acos((clamp(trace(R_hat_i R_i^T), -1, 3) - 1) / 2) * 180 / pi   (degrees)
+ * R, R_hat: rotation matrices, row-major, `stride` floats apart (9 for packed (n,3,3) arrays, 16 to
+ * read the rotation block of (n,4,4) transforms in place). */
+int ume_rotation_error_deg_f32(const float* R, const float* R_hat, int64_t n, int stride_R, int stride_R_hat,
+                               float* out, void* stream);
+
+/* ---------------------------------------------------------------- match sub-sampling
+ * Replaces evaluate.py:233-245 (`filter_by_ume_dist_cond`): draw k of the n matches of every pair
+ * WITHOUT replacement with probability proportional to exp((1 - d) / tau), which the reference does
+ * on the host with np.random.choice (a D2H copy and a sync per pair).  Gumbel-top-k: the k largest
+ * of (1 - d)/tau - log(-log u), u ~ U(0,1) from Philox4x32-10 keyed by (seed, pair, match), or taken
+ * from `u` (B,n) when it is not NULL (parity tests feed the uniforms in as data).
+ *   d (B,n) match distances -> idx (B,k) int64: the selected matches in ascending order.
+ * Same distribution as the reference's sampler, not the same random stream.  Limits: n <= 49152. */
+int ume_gumbel_topk_f32(const float* d, const float* u, int B, int n, int k, float tau, uint64_t seed,
+                        int64_t* idx, void* stream);
+
 /* ---------------------------------------------------------------- nearest-neighbour feature transfer
  * Replaces pytorch3d.ops.knn_points(K=1) + knn_gather at evaluate.py:272-275.
  *   q (B,P1,3) queries, p (B,P2,3) cloud, x (B,P2,U) features of p (may be NULL)

@@ -24,7 +24,7 @@ REPO = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, REPO)
 sys.path.insert(0, HERE)
 
-from ref_import import import_reference  # noqa: E402
+from oracle.ref_import import import_reference  # noqa: E402
 from umeregrobust_b200 import synth  # noqa: E402
 from oracle import pytorch3d_ops as p3d  # noqa: E402
 
@@ -116,6 +116,21 @@ def golden_kp_layer(ref_loc):
     return out
 
 
+def golden_kp_layer_nrand(ref_loc):
+    """ume_kp_layer.forward with n_rand (utils/loc_utils.py:406-410: sums of random triplets of the
+    diagonal pairs; host RNG np.random.choice, seeded here so that the draw is reproducible)."""
+    p = small_pair(203, 2048, 16, 24, exact_copy=False)
+    layer = ref_loc.ume_kp_layer(ume_knn=48, ume_desc_rad=3.0, diag_only=True, n_rand=40)
+    np.random.seed(7)
+    with torch.no_grad():
+        T, D, G_kp, H_kp = layer(t(p["src_pts"])[None], t(p["src_feat"])[None], t(p["src_kp"])[None],
+                                 t(p["tgt_pts"])[None], t(p["tgt_feat"])[None], t(p["tgt_kp"])[None])
+    out = dict(p, ume_knn=np.int64(48), ume_desc_rad=np.float32(3.0), n_rand=np.int64(40), np_seed=np.int64(7),
+               T=T.numpy(), D=D.numpy(), G=G_kp.numpy(), H=H_kp.numpy())
+    np.savez_compressed(os.path.join(HERE, "kp_layer_nrand.npz"), **out)
+    return out
+
+
 def golden_rigid_random(ref_loc):
     """batch_estimate_transform_ume_old on random well-conditioned (G,H) pairs for C in {8,32,64}:
     H built from G by a known rigid 'D' matrix so the answer is also known analytically."""
@@ -195,4 +210,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "kp_layer_nrand":      # add one fixture without touching the others
+        torch.manual_seed(0)
+        torch.set_num_threads(1)
+        golden_kp_layer_nrand(import_reference()[1])
+    else:
+        main()

@@ -17,7 +17,7 @@ REPO = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, REPO)
 sys.path.insert(0, HERE)
 
-from ref_import import import_reference, REF_ROOT  # noqa: E402
+from oracle.ref_import import import_reference, REF_ROOT  # noqa: E402
 from umeregrobust_b200 import synth  # noqa: E402
 
 

@@ -83,16 +83,44 @@ def test_wrappers_refuse_cpu_tensors():
 def test_patch_reference_rebinds_names():
     import types
     import umeregrobust_b200 as ume
+    from umeregrobust_b200 import training
     fake_eval = types.ModuleType("evaluate")
     fake_loc = types.ModuleType("utils.loc_utils")
+    fake_loss = types.ModuleType("loss")
+    names = ("ball_query", "knn_points", "knn_gather", "ume_cdist", "batch_estimate_transform_ume_old", "ume_kp_layer")
     for m in (fake_eval, fake_loc):
-        for n in ("ball_query", "knn_points", "knn_gather", "ume_cdist", "batch_estimate_transform_ume_old", "ume_kp_layer"):
+        for n in names:
             setattr(m, n, object())
     fake_eval.my_ume_generation = object()
-    done = ume.patch_reference(fake_eval, fake_loc)
-    assert fake_eval.my_ume_generation is ume.my_ume_generation
-    assert fake_loc.ume_cdist is ume.ume_cdist and fake_eval.ball_query is ume.ball_query
-    assert ("evaluate", "my_ume_generation") in done and len(done) == 13
+    for n in ("generate_ume_from_keypoints2", "UMEContrastiveLoss", "CubeRegistrationLoss", "ume_cdist"):
+        setattr(fake_loss, n, object())
+    fake_loc.generate_ume_from_keypoints2 = object()
+    loc_before = {n: getattr(fake_loc, n) for n in names}
+    try:
+        # default: `evaluate` only, and the distance test in pytorch3d's CUDA arithmetic (FMA)
+        done = ume.patch_reference(fake_eval, fake_loc)
+        assert fake_eval.my_ume_generation is ume.my_ume_generation and fake_eval.ball_query is ume.ball_query
+        assert all(getattr(fake_loc, n) is v for n, v in loc_before.items())      # the losses import from here: untouched
+        assert ("evaluate", "my_ume_generation") in done and len(done) == 7
+        assert ume.config["fma_dist"] is True
+        # opt-in: the inference kernels inside utils.loc_utils too
+        done = ume.patch_reference(fake_eval, fake_loc, fma_dist=False, patch_loc_utils=True)
+        assert fake_loc.ume_cdist is ume.ume_cdist and ("utils.loc_utils", "ume_cdist") in done
+        assert ume.config["fma_dist"] is False
+        # training: differentiable mirrors into utils.loc_utils / loss, nothing without autograd
+        for n, v in loc_before.items():
+            setattr(fake_loc, n, v)
+        done = ume.patch_reference(fake_eval, fake_loc, training=True, loss_module=fake_loss)
+        assert fake_loss.UMEContrastiveLoss is training.UMEContrastiveLoss
+        assert fake_loss.CubeRegistrationLoss is training.CubeRegistrationLoss
+        assert fake_loc.generate_ume_from_keypoints2 is training.generate_ume_from_keypoints2
+        assert fake_loc.ume_cdist is loc_before["ume_cdist"] and not isinstance(fake_loss.ume_cdist, types.FunctionType)
+        with pytest.raises(ValueError):
+            ume.patch_reference(fake_eval, fake_loc, patch_loc_utils=True, training=True)
+        with pytest.raises(RuntimeError):
+            ume.patch_reference(None, None)
+    finally:
+        ume.config["fma_dist"] = False
 
 
 def test_new_entry_points_validate_without_a_device(handle):

@@ -1,5 +1,5 @@
 """CPU, build container only: the oracle against the UNMODIFIED reference run live (imported from
-/root/reference under the stubs of tests/golden/ref_import.py) on fresh seeded inputs — more pins
+/root/reference under the stubs of oracle/ref_import.py) on fresh seeded inputs — more pins
 than the frozen golden files.  Skipped wherever the reference tree is absent (the GPU box)."""
 import os
 import sys
@@ -10,9 +10,7 @@ import pytest
 
 torch = pytest.importorskip("torch")
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(HERE, "golden"))
-import ref_import  # noqa: E402
+from oracle import ref_import  # noqa: E402
 
 from oracle import ume_oracle as orc  # noqa: E402
 from umeregrobust_b200 import synth  # noqa: E402

@@ -94,6 +94,8 @@ def _bind(lib):
         "ume_cdist_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]),
         "ume_pair_dist_f32": (i32, [vp, vp, i64, i32, f32, vp, vp]),
         "ume_rigid_solve_f32": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+        "ume_rotation_error_deg_f32": (i32, [vp, vp, i64, i32, i32, vp, vp]),
+        "ume_gumbel_topk_f32": (i32, [vp, vp, i32, i32, i32, f32, c.c_uint64, vp, vp]),
         "ume_knn1_workspace_bytes": (sz, [i32, i32, i32]),
         "ume_knn1_gather_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, u32, vp, vp, vp, vp, sz, vp]),
         "ume_knn_workspace_bytes": (sz, [i32, i32, i32]),
@@ -123,7 +125,8 @@ EXPORTED_SYMBOLS = ["ume_abi_version", "ume_last_error", "ume_status_string", "u
                     "ume_feature_spatial_var_workspace_bytes", "ume_feature_spatial_var_f32", "ume_weight_features_f32",
                     "ume_corr_scores_workspace_bytes", "ume_corr_scores_f32",
                     "ume_voxel_unique_workspace_bytes", "ume_voxel_unique_f32",
-                    "ume_moments_backward_f32", "ume_neighbor_count_f32", "ume_linear_sum_assignment_host_f32"]
+                    "ume_moments_backward_f32", "ume_neighbor_count_f32", "ume_linear_sum_assignment_host_f32",
+                    "ume_rotation_error_deg_f32", "ume_gumbel_topk_f32"]
 
 
 def lib():

@@ -7,6 +7,7 @@ streams and nothing else.  Inputs must be CUDA tensors: there is no CPU fallback
 """
 import collections
 import ctypes
+import threading
 
 import torch
 
@@ -26,6 +27,7 @@ _KNN = collections.namedtuple("_KNN", ["dists", "idx", "knn"])
 config = {"fma_dist": False, "cell_div2": False, "cdist_impl": None, "cta_moments": False, "warp_moments": False}
 
 _workspaces = {}
+_workspaces_lock = threading.Lock()
 
 
 def _flags():
@@ -42,15 +44,31 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _workspace(nbytes, device):
-    """Per (device, stream) scratch buffer, grown on demand.  Calls are stream-ordered, so reuse
-    by consecutive calls on the same stream is safe."""
+def _workspace(nbytes, device, buf=None):
+    """Scratch buffer for one call, grown on demand.  With an arena dict `buf` the workspace belongs
+    to that arena (an engine, a captured graph): nothing else ever touches it.  Without, it is a
+    per (device, stream) buffer — calls are stream-ordered, so reuse by consecutive calls on the same
+    stream is safe; the table is guarded by a lock and a stream's buffer is only ever replaced by
+    a larger one."""
+    if buf is not None:
+        ws = buf.get("_ws")
+        if ws is None or ws.numel() < nbytes or ws.device != device:
+            ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+            buf["_ws"] = ws
+        return ws
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
-    return ws
+    with _workspaces_lock:
+        ws = _workspaces.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+            _workspaces[key] = ws
+        return ws
+
+
+def release_workspaces():
+    """Drop every per-stream scratch buffer (they are otherwise kept for the life of the process)."""
+    with _workspaces_lock:
+        _workspaces.clear()
 
 
 def _out(buf, key, shape, dtype, device):
@@ -72,6 +90,9 @@ def _dev_f32(t, name, ndim=None):
         raise RuntimeError("%s is on %s: umeregrobust_b200 only runs on CUDA devices (no CPU fallback)" % (name, t.device))
     if ndim is not None and t.dim() != ndim:
         raise ValueError("%s must have %d dims, got shape %s" % (name, ndim, tuple(t.shape)))
+    if t.requires_grad and torch.is_grad_enabled():
+        raise RuntimeError("%s requires grad: the inference kernels of umeregrobust_b200 are not differentiable; use the "
+                           "autograd mirrors in umeregrobust_b200.training (or wrap the call in torch.no_grad())" % name)
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
@@ -202,7 +223,7 @@ def ume_moments(pts, kpts, feat, K, radius, return_centered=False, return_count=
     cnt = _out(buf, "cnt" + tag, (B, n), torch.int32, dev) if return_count else None
     with torch.cuda.device(dev):
         L = _lib.lib()
-        ws = _workspace(L.ume_moments_workspace_bytes(B, N, n, C, int(K)), dev)
+        ws = _workspace(L.ume_moments_workspace_bytes(B, N, n, C, int(K)), dev, buf)
         rc = L.ume_moments_f32(_ptr(pts), _ptr(kpts), _ptr(feat), B, N, n, C, int(K), float(radius),
                                _flags() | (_lib.UME_FLAG_RAW_MOMENTS if raw else 0),
                                _ptr(F), _ptr(Fc), _ptr(cnt), _ptr(ws), ws.numel(), _stream())
@@ -304,7 +325,7 @@ def descriptor_cdist(Qt1, Qt2, want_D=True, want_argmin=False, impl=None, buf=No
     with torch.cuda.device(dev):
         L = _lib.lib()
         nbytes = L.ume_cdist_workspace_bytes(B, n1, n2, C, impl)
-        ws = _workspace(nbytes, dev) if nbytes else None
+        ws = _workspace(nbytes, dev, buf) if nbytes else None
         rc = L.ume_cdist_f32(_ptr(Qt1), _ptr(Qt2), B, n1, n2, C, impl, _ptr(D), _ptr(am), _ptr(dm), _ptr(ws),
                              ws.numel() if ws is not None else 0, _stream())
     _lib.check(rc, "descriptor_cdist")
@@ -367,12 +388,30 @@ def batch_estimate_transform_ume_old(G, H):
     return T, Dp
 
 
+def _rot_operand(R, name):
+    """(pointer-ready tensor, stride in floats) of a batch of 3x3 rotations: packed (n,3,3) arrays and
+    the rotation blocks of (n,4,4) transforms (`T[:, :3, :3]`) are read in place."""
+    if not isinstance(R, torch.Tensor) or R.dim() != 3 or tuple(R.shape[1:]) != (3, 3):
+        raise ValueError("%s must be (B,3,3), got %s" % (name, tuple(getattr(R, "shape", ()))))
+    if not R.is_cuda:
+        raise RuntimeError("%s is on %s: umeregrobust_b200 only runs on CUDA devices (no CPU fallback)" % (name, R.device))
+    if R.dtype == torch.float32 and R.stride(1) == 4 and R.stride(2) == 1 and (R.shape[0] <= 1 or R.stride(0) == 16):
+        return R, 16
+    return R.float().contiguous(), 9
+
+
 def relative_rotation_error(R, R_hat):
-    """utils/eval_utils.py:60-76: degrees, acos((clamp(tr(R_hat R^T), -1, 3) - 1) / 2).  A handful
-    of elementwise torch ops on (B,3,3); a metric, not part of the measured path."""
-    delta = torch.matmul(R_hat, torch.transpose(R, 1, 2))
-    tr = torch.clamp(torch.einsum("bii->b", delta), -1, 3)
-    return torch.acos((tr - 1) / 2) * (180 / torch.tensor(3.141592653589793))
+    """utils/eval_utils.py:60-76: degrees, acos((clamp(tr(R_hat R^T), -1, 3) - 1) / 2) * 180/pi.
+    R, R_hat (B,3,3) on the device (views into (B,4,4) transforms are read in place) -> (B,)."""
+    R, sr = _rot_operand(R, "R")
+    R_hat, sh = _rot_operand(R_hat, "R_hat")
+    if R.shape[0] != R_hat.shape[0]:
+        raise ValueError("relative_rotation_error: batch sizes differ")
+    out = torch.empty((R.shape[0],), dtype=torch.float32, device=R.device)
+    with torch.cuda.device(R.device):
+        rc = _lib.lib().ume_rotation_error_deg_f32(_ptr(R), _ptr(R_hat), R.shape[0], sr, sh, _ptr(out), _stream())
+    _lib.check(rc, "relative_rotation_error")
+    return out
 
 
 # ----------------------------------------------------------------------------- ume_kp_layer
@@ -635,27 +674,44 @@ def hungarian_match(D):
 
 
 # ----------------------------------------------------------------------------- match sub-sampling (f2)
-def weighted_match_subsample(ume_d, tau, num_samples, generator=None):
+_subsample_calls = [0]
+
+
+def weighted_match_subsample(ume_d, tau, num_samples, generator=None, u=None, seed=None, buf=None):
     """Device-side equivalent of evaluate.py:233-245: draw `num_samples` of the n matches WITHOUT
     replacement with probability proportional to exp((1 - d) / tau).  The reference does this on
-    the host with np.random.choice (a D2H sync per pair); here it is the Gumbel-top-k trick on the
-    device — the same distribution (successive sampling without replacement == top-k of
-    log-weight + Gumbel noise), but not the same random stream, so parity tests feed `cond` in as
-    data.  ume_d (n,) or (B,n) -> int64 indices (num_samples,) or (B,num_samples), unordered like
-    np.random.choice's result.  Uses torch's RNG and top-k (glue between two kernels of the path,
-    not a measured stage)."""
-    d = ume_d if ume_d.dim() == 2 else ume_d[None]
-    k = min(int(num_samples), d.shape[-1])
-    logw = (1.0 - d.float()) / float(tau)
-    u = torch.rand(d.shape, device=d.device, generator=generator).clamp_(min=1e-20, max=1.0 - 1e-7)
-    keys = logw - torch.log(-torch.log(u))
-    idx = torch.topk(keys, k, dim=-1, sorted=False).indices
+    the host with np.random.choice (a D2H sync per pair); here it is the Gumbel-top-k trick in one
+    kernel (`ume_gumbel_topk_f32`: Philox counter RNG, exact radix select per pair) — the same
+    distribution (successive sampling without replacement == top-k of log-weight + Gumbel noise), but
+    not the same random stream, so parity tests feed the uniforms `u` (same shape as ume_d) in as data.
+    ume_d (n,) or (B,n) -> int64 indices (num_samples,) or (B,num_samples), ascending.
+    `seed`: Philox key; default: drawn from `generator` (a CPU torch.Generator) or derived from
+    torch.initial_seed() and a call counter, so that torch.manual_seed() makes runs repeatable."""
+    d = _dev_f32(ume_d if ume_d.dim() == 2 else ume_d[None], "ume_d", 2)
+    B, n = d.shape
+    k = min(int(num_samples), n)
+    if u is not None:
+        u = _dev_f32(u if u.dim() == 2 else u[None], "u", 2)
+        if tuple(u.shape) != (B, n):
+            raise ValueError("weighted_match_subsample: u %s does not match ume_d %s" % (tuple(u.shape), (B, n)))
+    if seed is None:
+        if generator is not None:
+            seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator if generator.device.type == "cpu" else None).item())
+        else:
+            _subsample_calls[0] += 1
+            seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _subsample_calls[0]) & 0xFFFFFFFFFFFFFFFF
+    idx = _out(buf, "subsample_idx", (B, k), torch.int64, d.device)
+    with torch.cuda.device(d.device):
+        rc = _lib.lib().ume_gumbel_topk_f32(_ptr(d), _ptr(u), B, n, k, float(tau), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(idx),
+                                            _stream())
+    _lib.check(rc, "weighted_match_subsample")
     return idx if ume_d.dim() == 2 else idx[0]
 
 
 # ----------------------------------------------------------------------------- fused hot path
 def register_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K, radius, want_D=False,
-                        centered=True, buf=None, matching="argmin"):
+                        centered=True, buf=None, matching="argmin", subsample=None, tau=0.05, subsample_u=None,
+                        subsample_seed=None):
     """evaluate.py:206-257 for a whole batch, without the host-RNG sub-sampling (:233-245): UME
     matrices for both clouds, subspace distances with fused arg-min, one rigid hypothesis per
     source keypoint from its best-matching target keypoint.
@@ -667,6 +723,9 @@ def register_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K,
     the same shapes (the returned tensors are then only valid until that next call).
     matching="hungarian" (evaluate.py:216-222, `hungarian_matching_flag`): one-to-one matches from the
     host assignment solver instead of the row arg-min (one D2H copy of D per call, like the reference).
+    subsample=m (evaluate.py:233-245, `filter_by_ume_dist_cond` with ume_n_samples = m): the solve runs on
+    m of the n matches drawn without replacement with probability ~ exp((1 - d)/tau) on the device
+    (`weighted_match_subsample`); match / dmin / T then have m rows per pair.
     Returns dict(F_src, F_tgt, match (B,n,2) int64, dmin (B,n), T (B,n,4,4), D or None)."""
     if centered:
         F_src, Fc_src = ume_moments(src_pts, src_kp, src_feat, K, radius, return_centered=True, buf=buf, tag="_src")
@@ -686,6 +745,14 @@ def register_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K,
         T = rigid_solve(A, Bm, gi, hi, src_kp if centered else None, tgt_kp if centered else None, buf=buf)
         dsel = torch.gather(torch.gather(D, 1, gi[..., None].expand(-1, -1, D.shape[2])), 2, hi[..., None])[..., 0]
         return dict(F_src=F_src, F_tgt=F_tgt, match=m, dmin=dsel, T=T, D=D)
+    if subsample is not None and int(subsample) < am.shape[1]:
+        sel = weighted_match_subsample(dm, tau, int(subsample), u=subsample_u, seed=subsample_seed, buf=buf)   # (B,m) ascending
+        hi_sel = torch.gather(am, 1, sel)
+        T = rigid_solve(A, Bm, sel, hi_sel, src_kp if centered else None, tgt_kp if centered else None, buf=buf)
+        match = _out(buf, "match_sub", tuple(sel.shape) + (2,), torch.int64, am.device)
+        match[..., 0] = sel
+        match[..., 1] = hi_sel
+        return dict(F_src=F_src, F_tgt=F_tgt, match=match, dmin=torch.gather(dm, 1, sel), T=T, D=D)
     if centered:
         T = rigid_solve(A, Bm, None, am, src_kp, tgt_kp, buf=buf)
     else:

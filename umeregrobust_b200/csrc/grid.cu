@@ -134,55 +134,93 @@ UME_DEVI bool point_cell(const GridHeader& h, float x, float y, float z, int* ce
 
 
 // ---------------------------------------------------------------- binning
-// Global atomics per point were the bottleneck of the first version (7.7 M contended L2 atomics
-// per pass, ~0.5 ms per build at batch 64).  Now each CTA owns a contiguous slice of one cloud and
-// ranks its points inside a shared-memory histogram (one smem atomic per point); only the
-// non-empty bins touch global memory (one atomicAdd per bin reserves the CTA's range inside the
-// cell), and the scatter pass needs no atomics at all: position = cell_start + rank.
+// A STABLE counting sort by cell: inside a cell the points keep their row order, so the sorted array —
+// and with it every sum the moment kernels form by walking it — is a pure function of the input
+// (bit-reproducible from launch to launch; the first version ranked with shared-memory atomics and
+// was not).  Each CTA owns a contiguous slice of one cloud and a shared-memory histogram:
+//   * a warp owns kRankRun * 32 CONSECUTIVE rows of every tile; equal cells inside a group of 32 are
+//     ranked with match.any (lower lane first);
+//   * the warps of a tile update the histogram one after the other, in row order (one CTA barrier per
+//     turn; the point loads and the cell arithmetic of the whole tile are done before the turns start);
+//   * the CTA's per-cell counts go to a (slice, cell) table; the scan kernel turns them into
+//     cell_start[] and, in place, into every slice's first slot inside each cell.
+// No global atomics, no memset, and the scatter pass is position = slice_base[slice][cell] + rank.
 constexpr int kRankThreads = 512;
+constexpr int kRankWarps = kRankThreads / 32;
+constexpr int kRankRun = 4;                                   // groups of 32 consecutive rows per warp and tile
+constexpr int kRankTile = kRankThreads * kRankRun;
+
+// slices per cloud: about four CTAs per SM in total, at least ~2048 rows per slice
+static int grid_slices(int B, int N) {
+    int G = (4 * 148) / (B > 0 ? B : 1);
+    const int cap = N / 2048 < 64 ? N / 2048 : 64;
+    if (G > cap) G = cap;
+    return G < 1 ? 1 : G;
+}
 
 __global__ void __launch_bounds__(kRankThreads)
-grid_rank_kernel(const float* __restrict__ pts, int N, const GridHeader* __restrict__ hdr, int* __restrict__ g_count,
-                 int cells_cap, int* __restrict__ cell_of, int* __restrict__ rank_of) {
+grid_rank_kernel(const float* __restrict__ pts, int N, int per, const GridHeader* __restrict__ hdr,
+                 int* __restrict__ slice_cnt, int cells_cap, int* __restrict__ cell_of, int* __restrict__ rank_of) {
     extern __shared__ int s_hist[];
     const int b = blockIdx.y, G = gridDim.x, g = blockIdx.x;
     const GridHeader h = hdr[b];
     const int ncells = h.ncells;
-    const int lo = (int)((int64_t)N * g / G), hi = (int)((int64_t)N * (g + 1) / G);
+    const int lo = min(N, g * per), hi = min(N, lo + per);
     const float* pb = pts + (size_t)b * N * 3;
     int* cell_b = cell_of + (size_t)b * N;
     int* rank_b = rank_of + (size_t)b * N;
-    int* cnt_b = g_count + (size_t)b * cells_cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = lanemask_lt();
     for (int c = threadIdx.x; c < ncells; c += kRankThreads) s_hist[c] = 0;
     __syncthreads();
-    for (int i = lo + threadIdx.x; i < hi; i += kRankThreads) {
-        const float x = pb[i * 3 + 0], y = pb[i * 3 + 1], z = pb[i * 3 + 2];
-        int cell;
-        if (point_cell(h, x, y, z, &cell)) {
-            cell_b[i] = cell;
-            rank_b[i] = atomicAdd(&s_hist[cell], 1);
-        } else {
-            cell_b[i] = -1;
+    for (int t0 = lo; t0 < hi; t0 += kRankTile) {
+        // this warp's rows of the tile: t0 + warp * (32 * kRankRun) + 32 r + lane
+        int cell[kRankRun], intra[kRankRun], grp[kRankRun];
+        const int w0 = t0 + warp * (32 * kRankRun);
+#pragma unroll
+        for (int r = 0; r < kRankRun; ++r) {
+            const int i = w0 + 32 * r + lane;
+            int c = -1;
+            if (i < hi) {
+                const float x = pb[(size_t)i * 3 + 0], y = pb[(size_t)i * 3 + 1], z = pb[(size_t)i * 3 + 2];
+                if (!point_cell(h, x, y, z, &c)) c = -1;
+                cell_b[i] = c;
+            }
+            cell[r] = c;
+            const unsigned peers = __match_any_sync(UME_FULL_MASK, c);
+            intra[r] = __popc(peers & lt);
+            grp[r] = (intra[r] == 0) ? __popc(peers) : 0;      // the group's first lane carries its size
+        }
+        int base[kRankRun];
+        for (int turn = 0; turn < kRankWarps; ++turn) {        // row order: warp 0's rows come first
+            if (turn == warp) {
+#pragma unroll
+                for (int r = 0; r < kRankRun; ++r) {
+                    base[r] = (cell[r] >= 0) ? s_hist[cell[r]] : 0;
+                    __syncwarp();
+                    if (cell[r] >= 0 && grp[r]) s_hist[cell[r]] = base[r] + grp[r];
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int r = 0; r < kRankRun; ++r) {
+            const int i = w0 + 32 * r + lane;
+            if (i < hi && cell[r] >= 0) rank_b[i] = base[r] + intra[r];
         }
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < ncells; c += kRankThreads) {
-        const int cnt = s_hist[c];
-        if (cnt) s_hist[c] = atomicAdd(&cnt_b[c], cnt);      // this CTA's first slot inside cell c
-    }
-    __syncthreads();
-    for (int i = lo + threadIdx.x; i < hi; i += kRankThreads) {   // same thread wrote cell_b[i] / rank_b[i]
-        const int c = cell_b[i];
-        if (c >= 0) rank_b[i] += s_hist[c];
-    }
+    int* out = slice_cnt + ((size_t)b * G + g) * cells_cap;
+    for (int c = threadIdx.x; c < ncells; c += kRankThreads) out[c] = s_hist[c];
 }
 
-// One CTA per cloud: exclusive scan of the per-cell counts over the cells in use.
-__global__ void __launch_bounds__(1024) grid_scan_kernel(const int* __restrict__ g_count, int* __restrict__ cell_start,
+// One CTA per cloud: per-cell totals over the slices, exclusive scan over the cells in use
+// (cell_start), and in place the first slot of every slice inside each cell.
+__global__ void __launch_bounds__(1024) grid_scan_kernel(int* __restrict__ slice_cnt, int G, int* __restrict__ cell_start,
                                                          GridHeader* __restrict__ hdr, int cells_cap) {
     const int b = blockIdx.x;
     const int ncells = hdr[b].ncells;
-    const int* cnt = g_count + (size_t)b * cells_cap;
+    int* tab = slice_cnt + (size_t)b * G * cells_cap;
     int* cs = cell_start + (size_t)b * (cells_cap + 1);
     __shared__ int warp_tot[32];
     __shared__ int running;
@@ -191,7 +229,9 @@ __global__ void __launch_bounds__(1024) grid_scan_kernel(const int* __restrict__
     __syncthreads();
     for (int base = 0; base < ncells; base += 1024) {
         const int c = base + t;
-        const int v = (c < ncells) ? cnt[c] : 0;
+        int v = 0;
+        if (c < ncells)
+            for (int g = 0; g < G; ++g) v += tab[(size_t)g * cells_cap + c];
         int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -203,7 +243,15 @@ __global__ void __launch_bounds__(1024) grid_scan_kernel(const int* __restrict__
         int wbase = 0;
         for (int k = 0; k < w; ++k) wbase += warp_tot[k];
         const int run0 = running;
-        if (c < ncells) cs[c] = run0 + wbase + incl - v;
+        if (c < ncells) {
+            int at = run0 + wbase + incl - v;
+            cs[c] = at;
+            for (int g = 0; g < G; ++g) {
+                const int n = tab[(size_t)g * cells_cap + c];
+                tab[(size_t)g * cells_cap + c] = at;
+                at += n;
+            }
+        }
         __syncthreads();
         if (t == 1023) running = run0 + wbase + incl;
         __syncthreads();
@@ -214,17 +262,17 @@ __global__ void __launch_bounds__(1024) grid_scan_kernel(const int* __restrict__
     }
 }
 
-__global__ void grid_scatter_kernel(const float* __restrict__ pts, int N, const int* __restrict__ cell_start, int cells_cap,
-                                    const int* __restrict__ cell_of, const int* __restrict__ rank_of,
+__global__ void grid_scatter_kernel(const float* __restrict__ pts, int N, int per, int G, const int* __restrict__ slice_base,
+                                    int cells_cap, const int* __restrict__ cell_of, const int* __restrict__ rank_of,
                                     float4* __restrict__ sorted) {
     const int b = blockIdx.y;
     const float* pb = pts + (size_t)b * N * 3;
-    const int* cs = cell_start + (size_t)b * (cells_cap + 1);
+    const int* tab = slice_base + (size_t)b * G * cells_cap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const int c = cell_of[(size_t)b * N + i];
         if (c >= 0) {
-            const int pos = __ldg(&cs[c]) + rank_of[(size_t)b * N + i];
-            sorted[(size_t)b * N + pos] = make_float4(pb[i * 3 + 0], pb[i * 3 + 1], pb[i * 3 + 2], __int_as_float(i));
+            const int pos = __ldg(&tab[(size_t)(i / per) * cells_cap + c]) + rank_of[(size_t)b * N + i];
+            sorted[(size_t)b * N + pos] = make_float4(pb[(size_t)i * 3 + 0], pb[(size_t)i * 3 + 1], pb[(size_t)i * 3 + 2], __int_as_float(i));
         }
     }
 }
@@ -235,7 +283,7 @@ size_t grid_workspace_bytes(int B, int N, int cells_cap) {
     size_t s = 0;
     s = align_up(s, 256) + (size_t)B * sizeof(GridHeader);
     s = align_up(s, 256) + (size_t)B * 6 * sizeof(int);
-    s = align_up(s, 256) + (size_t)B * cells_cap * sizeof(int);
+    s = align_up(s, 256) + (size_t)B * grid_slices(B, N) * cells_cap * sizeof(int);
     s = align_up(s, 256) + (size_t)B * (cells_cap + 1) * sizeof(int);
     s = align_up(s, 256) + (size_t)B * N * sizeof(int);
     s = align_up(s, 256) + (size_t)B * N * sizeof(int);
@@ -245,9 +293,11 @@ size_t grid_workspace_bytes(int B, int N, int cells_cap) {
 
 int grid_build(const float* pts, const float* q, int B, int N, int nq, float expand, float cell,
                int cells_cap, Workspace& ws, GridView* view, cudaStream_t stream) {
+    const int G = grid_slices(B, N);
+    const int per = (N + G - 1) / G;
     GridHeader* hdr = ws.take<GridHeader>(B);
     int* bbox = ws.take<int>((size_t)B * 6);
-    int* g_count = ws.take<int>((size_t)B * cells_cap);
+    int* slice_cnt = ws.take<int>((size_t)B * G * cells_cap);
     int* cell_start = ws.take<int>((size_t)B * (cells_cap + 1));
     int* cell_of = ws.take<int>((size_t)B * N);
     int* rank_of = ws.take<int>((size_t)B * N);
@@ -266,16 +316,12 @@ int grid_build(const float* pts, const float* q, int B, int N, int nq, float exp
         grid_bbox_kernel<<<g, 256, 0, stream>>>(q, nq, bbox);
     }
     grid_params_kernel<<<(B + 127) / 128, 128, 0, stream>>>(bbox, hdr, B, expand, cell, cells_cap, N);
-    cudaMemsetAsync(g_count, 0, (size_t)B * cells_cap * sizeof(int), stream);
-    // CTAs per cloud: about two waves of the 148 SMs in total, at least ~2048 points per CTA
-    int G = (4 * 148) / B;
-    G = max(1, min(G, min(64, N / 2048)));
-    grid_rank_kernel<<<dim3((unsigned)G, (unsigned)B), kRankThreads, smem, stream>>>(pts, N, hdr, g_count, cells_cap, cell_of,
-                                                                                   rank_of);
-    grid_scan_kernel<<<B, 1024, 0, stream>>>(g_count, cell_start, hdr, cells_cap);
+    grid_rank_kernel<<<dim3((unsigned)G, (unsigned)B), kRankThreads, smem, stream>>>(pts, N, per, hdr, slice_cnt, cells_cap,
+                                                                                   cell_of, rank_of);
+    grid_scan_kernel<<<B, 1024, 0, stream>>>(slice_cnt, G, cell_start, hdr, cells_cap);
     dim3 gs((unsigned)min((N + 255) / 256, 296), (unsigned)B);
-    grid_scatter_kernel<<<gs, 256, 0, stream>>>(pts, N, cell_start, cells_cap, cell_of, rank_of, sorted);
-    count_launch(nq > 0 ? 7 : 6);
+    grid_scatter_kernel<<<gs, 256, 0, stream>>>(pts, N, per, G, slice_cnt, cells_cap, cell_of, rank_of, sorted);
+    count_launch(nq > 0 ? 6 : 5);
     view->hdr = hdr;
     view->cell_start = cell_start;
     view->sorted = sorted;

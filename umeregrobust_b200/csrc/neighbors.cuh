@@ -21,6 +21,8 @@ struct CollectSmem {
     int seg_prefix[kMaxRows + 1];
     int seg_chunk0[kMaxRows + 1];         // exclusive prefix of the rows' chunk counts
     unsigned chunk[kChunkCap];            // (position in the sorted array << 5) | (candidates - 1)
+    unsigned chunk_mask[kChunkCap];       // hit ballot of every chunk of the window (scan_mark)
+    int chunk_off[kChunkCap];             // list slot of the chunk's first hit (chunk_offsets)
     unsigned hist[kHistBins];
     unsigned bitmap[kBitmapWords];
     int warp_cnt[32];
@@ -28,15 +30,6 @@ struct CollectSmem {
     int sel_bin, sel_below, sel_T;
     int nrows, total, nchunks;
 };
-
-// shared-memory atomic add through PTX: keeps nvcc from wrapping a one-lane atomic in its own
-// warp-aggregation sequence (vote + find-leader + shuffle, ~16 instructions)
-UME_DEVI int smem_add(int* p, int v) {
-    int old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;"
-                 : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-    return old;
-}
 
 // One row's share of the chunk table for the window of chunk ids [w0, w0 + kChunkCap): the run
 // (start s, n candidates) is cut into pieces of 32; c0 = id of its first chunk.
@@ -108,12 +101,13 @@ UME_DEVI void row_run(const RowSetup& rs, const GridHeader& h, const int* __rest
 template <int NT>
 UME_DEVI void collect_rows(CollectSmem& sm, const GridHeader& h, const int* __restrict__ cs, float kx,
                            float ky, float kz, float radius) {
-    static_assert(NT >= 2 * kMaxRows, "one thread per candidate row, the others clear the histogram");
-    if (threadIdx.x < kMaxRows) {
+    static_assert(NT >= 2 * kMaxRows && kMaxRows == 64, "one thread per candidate row (two whole warps), the others clear the histogram");
+    const bool row_thread = threadIdx.x < kMaxRows;       // warp-uniform: kMaxRows is a multiple of 32
+    const int row = threadIdx.x;
+    int s = 0, n = 0, incl = 0, cincl = 0;
+    if (row_thread) {
         const RowSetup rs = row_setup(h, kx, ky, kz, radius);
         const int nrows = rs.nrows;
-        const int row = threadIdx.x;
-        int s = 0, n = 0;
         if (row < nrows) {
             row_run(rs, h, cs, kx, ky, kz, row, s, n);
             sm.seg_start[row] = s;
@@ -121,7 +115,8 @@ UME_DEVI void collect_rows(CollectSmem& sm, const GridHeader& h, const int* __re
         // inclusive prefixes of the run lengths and of the chunk counts over the (<= 64) rows: two
         // warps, shuffle scans, the second warp fixed up after the barrier
         const int lane = threadIdx.x & 31;
-        int incl = n, cincl = (n + 31) >> 5;
+        incl = n;
+        cincl = (n + 31) >> 5;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(UME_FULL_MASK, incl, o);
@@ -130,16 +125,17 @@ UME_DEVI void collect_rows(CollectSmem& sm, const GridHeader& h, const int* __re
         }
         if (threadIdx.x == 31) { sm.warp_cnt[0] = incl; sm.warp_cnt[1] = cincl; }
         if (threadIdx.x == 0) { sm.nrows = nrows; sm.count = 0; sm.seg_prefix[0] = 0; sm.seg_chunk0[0] = 0; }
-        __syncthreads();
+    } else {
+        // the warps without rows clear the row-index histogram the scan fills (select_kth_index)
+        for (int i = threadIdx.x - kMaxRows; i < kHistBins; i += NT - kMaxRows) sm.hist[i] = 0;
+    }
+    __syncthreads();                                       // one barrier, reached by every thread on the same path
+    if (row_thread) {
         if (threadIdx.x >= 32) { incl += sm.warp_cnt[0]; cincl += sm.warp_cnt[1]; }
         sm.seg_prefix[row + 1] = incl;
         sm.seg_chunk0[row + 1] = cincl;
         if (row == kMaxRows - 1) { sm.total = incl; sm.nchunks = cincl; }   // rows >= nrows are empty
         fill_chunks(sm, s, n, cincl - ((n + 31) >> 5), 0);
-    } else {
-        // the warps without rows clear the row-index histogram the scan fills (select_kth_index)
-        for (int i = threadIdx.x - kMaxRows; i < kHistBins; i += NT - kMaxRows) sm.hist[i] = 0;
-        __syncthreads();
     }
     __syncthreads();
 }
@@ -175,35 +171,24 @@ UME_DEVI void scan_candidates(const CollectSmem& sm, const float4* __restrict__ 
     }
 }
 
-// Warp-aggregated append of hits to list[0..cap); sm.count keeps counting past cap.
-UME_DEVI void append_hit(CollectSmem& sm, float4* list, int cap, bool hit, float ex, float ey, float ez, int idx) {
-    const unsigned m = __ballot_sync(UME_FULL_MASK, hit);
-    if (m) {
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(m) - 1;
-        int basepos = 0;
-        if (lane == leader) basepos = atomicAdd(&sm.count, __popc(m));
-        basepos = __shfl_sync(UME_FULL_MASK, basepos, leader);
-        if (hit) {
-            const int pos = basepos + __popc(m & lanemask_lt());
-            if (pos < cap) list[pos] = make_float4(ex, ey, ez, __int_as_float(idx));
-        }
-    }
-}
-
-// ---------------------------------------------------------------- first pass: warp-granular scan + append
+// ---------------------------------------------------------------- first pass: mark, offsets, fill
 // The candidates of the query are cut into chunks of <= 32 consecutive entries of one cell row
-// (chunk table, built once per query by the row threads).  Every warp takes chunks warp, warp + NW,
-// ...: two per iteration, the next two already loading while the current two are tested (four
-// 16-byte loads in flight per lane), one shared-memory atomic per iteration reserving the slots of
-// the hits of both.  Every hit is also counted in the histogram of (row index >> shift), whether or
-// not it still fits the list: level 1 of the counting select comes for free.  Trip counts differ between warps, so nothing in here may synchronise the CTA.
+// (chunk table, built once per query by the row threads).  The list must not depend on how the
+// warps happen to be scheduled — its order decides the order of the fp32 sums downstream, and the
+// results are meant to be bit-reproducible — so hits are placed at positions that are a pure
+// function of the chunk table:
+//   scan_mark      every warp takes chunks warp, warp + NW, ...: two per iteration, the next two
+//                  already loading (four 16-byte loads in flight per lane); exact distance test; the
+//                  chunk's hit ballot goes to chunk_mask[], every hit is counted in the histogram of
+//                  (row index >> shift): level 1 of the counting select comes for free;
+//   chunk_offsets  exclusive prefix of the ballots' populations = the slot of each chunk's first hit;
+//   scan_fill      chunks with hits are read again (L1 hits) and their hits written to their slots.
+// Trip counts differ between warps, so nothing inside scan_mark / scan_fill may synchronise the CTA.
 template <bool kFma, int NT>
-UME_DEVI void scan_append(CollectSmem& sm, float4* list, int cap, const float4* __restrict__ sorted_b, float kx,
-                          float ky, float kz, float r2, int nch, int shift) {
+UME_DEVI void scan_mark(CollectSmem& sm, const float4* __restrict__ sorted_b, float kx, float ky, float kz, float r2,
+                        int nch, int shift) {
     constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt = lanemask_lt();
     auto fetch = [&](int c, float4& v, int& cnt) {
         v = make_float4(0.f, 0.f, 0.f, 0.f);
         cnt = 0;
@@ -229,24 +214,80 @@ UME_DEVI void scan_append(CollectSmem& sm, float4* list, int cap, const float4* 
         const unsigned ma = __ballot_sync(UME_FULL_MASK, ha), mb = __ballot_sync(UME_FULL_MASK, hb);
         if (ha) atomicAdd(&sm.hist[__float_as_int(a.w) >> shift], 1u);     // level 1 of the counting select
         if (hb) atomicAdd(&sm.hist[__float_as_int(b.w) >> shift], 1u);
-        if (ma | mb) {
-            const int na_hits = __popc(ma);
-            int base = 0;
-            if (lane == 0) base = smem_add(&sm.count, na_hits + __popc(mb));
-            base = __shfl_sync(UME_FULL_MASK, base, 0);
-            const int sa = base + __popc(ma & lt), sb = base + na_hits + __popc(mb & lt);
-            if (ha && sa < cap) list[sa] = make_float4(ax, ay, az, a.w);
-            if (hb && sb < cap) list[sb] = make_float4(bx, by, bz, b.w);
+        if (lane == 0) {
+            sm.chunk_mask[c] = ma;
+            if (c + NW < nch) sm.chunk_mask[c + NW] = mb;
         }
         a = na; b = nb;
         ca = nca; cb = ncb;
     }
 }
 
+// chunk_off[c] = sm.count + hits of the chunks before c; sm.count += hits of the window.
+// Called by the whole CTA between two barriers of its own.
+template <int NT>
+UME_DEVI void chunk_offsets(CollectSmem& sm, int nch) {
+    static_assert(kChunkCap % NT == 0, "chunks per thread");
+    constexpr int per = kChunkCap / NT, NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();                                       // the window's ballots are visible
+    const int base = sm.count;
+    int v[per], s = 0;
+#pragma unroll
+    for (int i = 0; i < per; ++i) {
+        v[i] = (tid * per + i < nch) ? __popc(sm.chunk_mask[tid * per + i]) : 0;
+        s += v[i];
+    }
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(UME_FULL_MASK, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) sm.warp_cnt[warp] = incl;
+    __syncthreads();
+    int wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const int c = sm.warp_cnt[w];
+        if (w < warp) wbase += c;
+        tot += c;
+    }
+    int at = base + wbase + incl - s;
+#pragma unroll
+    for (int i = 0; i < per; ++i) {
+        if (tid * per + i < nch) sm.chunk_off[tid * per + i] = at;
+        at += v[i];
+    }
+    __syncthreads();                                       // everyone has read sm.count / warp_cnt
+    if (tid == 0) sm.count = base + tot;
+}
+
+template <int NT>
+UME_DEVI void scan_fill(const CollectSmem& sm, float4* list, int cap, const float4* __restrict__ sorted_b, float kx,
+                        float ky, float kz, int nch) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = lanemask_lt();
+#pragma unroll 2
+    for (int c = warp; c < nch; c += NW) {
+        const unsigned m = sm.chunk_mask[c];
+        const int off = sm.chunk_off[c];
+        if (m == 0u || off >= cap) continue;             // warp-uniform
+        if ((m >> lane) & 1u) {
+            const int pos = off + __popc(m & lt);
+            if (pos < cap) {
+                const float4 v = __ldg(&sorted_b[(sm.chunk[c] >> 5) + lane]);
+                list[pos] = make_float4(__fsub_rn(v.x, kx), __fsub_rn(v.y, ky), __fsub_rn(v.z, kz), v.w);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- counting select
 // Given that more than K candidates are in radius, find T = the K-th smallest row index among
 // them.  sm.hist already holds the histogram of (row index >> shift) over ALL in-radius candidates
-// (filled by scan_append, visible after a barrier).  `each(f)` must call f(row_index) once per
+// (filled by scan_mark, visible after a barrier).  `each(f)` must call f(row_index) once per
 // in-radius candidate (any thread, any order): it resolves the bin the K-th index falls in.
 template <int NT, typename Each>
 UME_DEVI int select_kth_index(CollectSmem& sm, int K, int shift, Each each) {
@@ -370,7 +411,10 @@ UME_DEVI int collect_neighbors(CollectSmem& sm, float4* list, int cap, const Gri
     const int nchunks = sm.nchunks;
     const int shift = max(0, 23 - __clz(N - 1));         // smallest shift with (N-1) >> shift < kHistBins
     for (int w0 = 0;;) {
-        scan_append<kFma, NT>(sm, list, cap, sorted_b, kx, ky, kz, r2, min(kChunkCap, nchunks - w0), shift);
+        const int nch = min(kChunkCap, nchunks - w0);
+        scan_mark<kFma, NT>(sm, sorted_b, kx, ky, kz, r2, nch, shift);
+        chunk_offsets<NT>(sm, nch);
+        scan_fill<NT>(sm, list, cap, sorted_b, kx, ky, kz, nch);
         w0 += kChunkCap;
         if (w0 >= nchunks) break;                        // the usual case: one window
         __syncthreads();
@@ -406,21 +450,30 @@ UME_DEVI int collect_neighbors(CollectSmem& sm, float4* list, int cap, const Gri
         });
     }
     __syncthreads();
-    if (threadIdx.x == 0) sm.count = 0;
-    __syncthreads();
-    int len = 0;   // block-uniform running length of the list (sm.count only hands out slots)
+    int len = 0;   // block-uniform running length of the list
     scan_candidates<kFma, NT>(sm, sorted_b, kx, ky, kz, r2,
                               [&](bool hit, float ex, float ey, float ez, float, int idx) {
+                                  // slots in thread order (prefix over the warps' ballots): the list, and with
+                                  // it the order of the sums, does not depend on the warps' timing
                                   const bool acc = hit && idx <= T;
-                                  const int n_acc = __syncthreads_count(acc);   // also orders the appends
+                                  const unsigned m = __ballot_sync(UME_FULL_MASK, acc);
+                                  const int warp = threadIdx.x >> 5;
+                                  if ((threadIdx.x & 31) == 0) sm.warp_cnt[warp] = __popc(m);
+                                  __syncthreads();
+                                  int wbase = 0, n_acc = 0;
+#pragma unroll
+                                  for (int w = 0; w < NT / 32; ++w) {
+                                      const int c = sm.warp_cnt[w];
+                                      if (w < warp) wbase += c;
+                                      n_acc += c;
+                                  }
+                                  __syncthreads();
                                   if (len + n_acc > cap) {
                                       flush(len, 0x7fffffff);
                                       __syncthreads();
-                                      if (threadIdx.x == 0) sm.count = 0;
-                                      __syncthreads();
                                       len = 0;
                                   }
-                                  append_hit(sm, list, cap, acc, ex, ey, ez, idx);
+                                  if (acc) list[len + wbase + __popc(m & lanemask_lt())] = make_float4(ex, ey, ez, __int_as_float(idx));
                                   len += n_acc;
                               });
     __syncthreads();

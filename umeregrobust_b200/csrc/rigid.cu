@@ -167,8 +167,42 @@ __global__ void __launch_bounds__(256) rigid_kernel(const float* __restrict__ G,
     }
 }
 
+// utils/eval_utils.py:60-76: one thread per pair of rotations.
+__global__ void rotation_error_kernel(const float* __restrict__ R, const float* __restrict__ Rh, int64_t n, int sr, int sh,
+                                      float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* a = R + i * sr;
+    const float* b = Rh + i * sh;
+    // trace(R_hat R^T) = sum_jk R_hat[j][k] R[j][k]   (the einsum of :66-67 after the matmul of :65)
+    float tr = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float row = 0.f;                                   // (R_hat R^T)[j][j], a 3-term dot as torch.matmul forms it
+#pragma unroll
+        for (int k = 0; k < 3; ++k) row = fmaf(b[j * 3 + k], a[j * 3 + k], row);
+        tr += row;
+    }
+    tr = fminf(fmaxf(tr, -1.f), 3.f);
+    out[i] = acosf((tr - 1.f) * 0.5f) * (180.f / 3.14159265358979323846f);
+}
+
 }  // namespace
 }  // namespace ume
+
+extern "C" int ume_rotation_error_deg_f32(const float* R, const float* R_hat, int64_t n, int stride_R, int stride_R_hat,
+                                          float* out, void* stream_) {
+    using namespace ume;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    UME_REQUIRE(n >= 0, UME_ERR_BAD_ARG, "ume_rotation_error_deg_f32: negative size");
+    if (n == 0) return UME_OK;
+    UME_REQUIRE(R && R_hat && out, UME_ERR_BAD_ARG, "ume_rotation_error_deg_f32: null pointer");
+    UME_REQUIRE(stride_R >= 9 && stride_R_hat >= 9, UME_ERR_BAD_ARG, "ume_rotation_error_deg_f32: stride < 9");
+    UME_REQUIRE((n + 255) / 256 < 0x7fffffffll, UME_ERR_UNSUPPORTED, "ume_rotation_error_deg_f32: too many rotations");
+    rotation_error_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(R, R_hat, n, stride_R, stride_R_hat, out);
+    count_launch();
+    return check_launch("rotation_error_kernel");
+}
 
 extern "C" int ume_rigid_solve_f32(const float* G, const float* H, const int64_t* gi, const int64_t* hi,
                                    const float* offG, const float* offH, int B, int nG, int nH, int nm, int C,

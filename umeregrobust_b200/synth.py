@@ -152,13 +152,31 @@ def _normalize_rows(x):
     return x / np.maximum(np.linalg.norm(x, axis=-1, keepdims=True), 1e-12)
 
 
+def _corresponding_rows(src_kp, tgt, gt, rng):
+    """Rows of `tgt` nearest to the images of the source keypoints under gt, in shuffled order: the same
+    physical locations seen in the other cloud (an independent sampling of the same surfaces)."""
+    from scipy.spatial import cKDTree
+    q = src_kp.astype(np.float64) @ gt[:3, :3].T + gt[:3, 3]
+    _, kt = cKDTree(tgt).query(q, k=1, workers=-1)
+    return kt[rng.permutation(len(kt))]
+
+
 def make_pair(seed, N=120000, C=32, n_kp=1024, model=KITTI, gt=None, exact_copy=False,
-              feat_noise=0.05, generator="lidar"):
+              feat_noise=0.05, generator="lidar", feat_model="iid", kp_mode="random", field_scale=0.3,
+              field_noise=0.2):
     """One registration pair.  Returns dict of float32 arrays:
     src_pts (N,3), src_feat (N,C), src_kp (n,3), src_kp_idx (n,), tgt_* likewise, gt (4,4).
 
     exact_copy=True: the target is the SAME points moved by gt with identical features and the
-    same keypoint rows (the exact-recovery known-answer case, BASELINE config #1)."""
+    same keypoint rows (the exact-recovery known-answer case, BASELINE config #1).
+    feat_model: "iid" = normalize(randn) per point, carried to the target by the nearest source point
+    (descriptors of DIFFERENT samplings of a surface are then unrelated, so only timing and
+    kernel-vs-oracle parity are meaningful); "field" = a smooth random field normalize(sin(W x + phi) +
+    noise) evaluated at every point of both clouds in the scene frame — what a backbone's output looks
+    like: two samplings of the same neighbourhood give nearly the same UME matrix, so matches and
+    per-match transforms are meaningful against the ground truth (BASELINE config #5's check).
+    kp_mode: "random" rows of each cloud (evaluate.py:199-204) or "corresponding" (the target keypoints
+    are the target rows nearest to the moved source keypoints)."""
     from scipy.spatial import cKDTree
     rng = np.random.default_rng(seed)
     scene = Scene(rng) if generator == "lidar" else None
@@ -167,7 +185,14 @@ def make_pair(seed, N=120000, C=32, n_kp=1024, model=KITTI, gt=None, exact_copy=
         gt = random_rigid(rng)
     gt = np.asarray(gt, dtype=np.float64)
     R, t = gt[:3, :3], gt[:3, 3]
-    src_feat = _normalize_rows(rng.normal(size=(N, C))).astype(np.float32)
+    if feat_model == "field":
+        W, phi = rng.normal(size=(3, C)) * field_scale, rng.uniform(0, 2 * np.pi, C)
+
+        def field(x):
+            return _normalize_rows(np.sin(x.astype(np.float64) @ W + phi) + field_noise * rng.normal(size=(len(x), C))).astype(np.float32)
+        src_feat = field(src)
+    else:
+        src_feat = _normalize_rows(rng.normal(size=(N, C))).astype(np.float32)
     if exact_copy:
         tgt = (src.astype(np.float64) @ R.T + t).astype(np.float32)
         tgt_feat = src_feat.copy()
@@ -175,17 +200,20 @@ def make_pair(seed, N=120000, C=32, n_kp=1024, model=KITTI, gt=None, exact_copy=
         kp_idx_t = kp_idx_s.copy()
     else:
         tgt_local = lidar_cloud(scene, rng, N, model) if scene is not None else disc_cloud(rng, N)
-        _, nn = cKDTree(src).query(tgt_local, k=1, workers=-1)
-        tgt_feat = _normalize_rows(src_feat[nn] + rng.normal(scale=feat_noise, size=(N, C))).astype(np.float32)
+        if feat_model == "field":
+            tgt_feat = field(tgt_local)
+        else:
+            _, nn = cKDTree(src).query(tgt_local, k=1, workers=-1)
+            tgt_feat = _normalize_rows(src_feat[nn] + rng.normal(scale=feat_noise, size=(N, C))).astype(np.float32)
         tgt = (tgt_local.astype(np.float64) @ R.T + t).astype(np.float32)
         kp_idx_s = rng.choice(N, n_kp, replace=False)
-        kp_idx_t = rng.choice(N, n_kp, replace=False)
+        kp_idx_t = _corresponding_rows(src[kp_idx_s], tgt, gt, rng) if kp_mode == "corresponding" else rng.choice(N, n_kp, replace=False)
     return dict(src_pts=src, src_feat=src_feat, src_kp=src[kp_idx_s].copy(), src_kp_idx=kp_idx_s,
                 tgt_pts=tgt, tgt_feat=tgt_feat, tgt_kp=tgt[kp_idx_t].copy(), tgt_kp_idx=kp_idx_t,
                 gt=gt.astype(np.float32))
 
 
-def rederive_pair(base, seed, n_kp=None, gt_extra=None):
+def rederive_pair(base, seed, n_kp=None, gt_extra=None, kp_mode="random"):
     """A cheap new pair from a generated one: fresh row permutations, fresh keypoints and an extra
     rigid motion of the target (features ride along with their rows).  Used to fill large batches
     without re-running the ray caster for every pair."""
@@ -197,7 +225,8 @@ def rederive_pair(base, seed, n_kp=None, gt_extra=None):
     gt = extra @ base["gt"].astype(np.float64)
     tgt = (base["tgt_pts"][pt].astype(np.float64) @ extra[:3, :3].T + extra[:3, 3]).astype(np.float32)
     src = base["src_pts"][ps]
-    ks, kt = rng.choice(N, n_kp, replace=False), rng.choice(N, n_kp, replace=False)
+    ks = rng.choice(N, n_kp, replace=False)
+    kt = _corresponding_rows(src[ks], tgt, gt, rng) if kp_mode == "corresponding" else rng.choice(N, n_kp, replace=False)
     return dict(src_pts=src, src_feat=base["src_feat"][ps], src_kp=src[ks].copy(), src_kp_idx=ks,
                 tgt_pts=tgt, tgt_feat=base["tgt_feat"][pt], tgt_kp=tgt[kt].copy(), tgt_kp_idx=kt,
                 gt=gt.astype(np.float32))
@@ -210,5 +239,6 @@ def make_batch(n_pairs, seed0=0, n_base=4, **kw):
     pairs = []
     for p in range(n_pairs):
         pairs.append(bases[p] if p < len(bases) else
-                     rederive_pair(bases[p % len(bases)], seed0 + 1000 + p, n_kp=kw.get("n_kp")))
+                     rederive_pair(bases[p % len(bases)], seed0 + 1000 + p, n_kp=kw.get("n_kp"),
+                                   kp_mode=kw.get("kp_mode", "random")))
     return {k: np.stack([q[k] for q in pairs], 0) for k in pairs[0]}
