@@ -145,8 +145,8 @@ int ume_rigid_solve_f32(const float* G, const float* H, const int64_t* gi, const
 
 /* Replaces utils/eval_utils.py:60-76 `relative_rotation_error(R, R_hat)`:
  *   out[i] = acos((clamp(trace(R_hat_i R_i^T), -1, 3) - 1) / 2) * 180 / pi   (degrees)
- * R, R_hat: rotation matrices, row-major, `stride` floats apart (9 for packed (n,3,3) arrays, 16 to
- * read the rotation block of (n,4,4) transforms in place). */
+ * R, R_hat: rotation matrices, row-major, `stride` floats apart: 9 = packed (n,3,3) arrays (row pitch 3),
+ * 16 = the rotation blocks of (n,4,4) transforms read in place (row pitch 4). */
 int ume_rotation_error_deg_f32(const float* R, const float* R_hat, int64_t n, int stride_R, int stride_R_hat,
                                float* out, void* stream);
 

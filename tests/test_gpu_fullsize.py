@@ -121,7 +121,7 @@ def test_config3_batch_properties(ume):
     b = synth.make_batch(8, seed0=31, n_base=2, N=120000, C=32, n_kp=1024)
     keys = ("src_pts", "src_feat", "src_kp", "tgt_pts", "tgt_feat", "tgt_kp")
     d = {k: dev(b[k]) for k in keys}
-    eng = RegistrationEngine(K=K_NN, radius=RADIUS, want_D=True, chunk_pairs=3)
+    eng = RegistrationEngine(K=K_NN, radius=RADIUS, want_D=True, chunk_pairs=4)
     out = eng.register(d)
     match = host(out["match"]).copy()
     D = host(out["D"]).copy()
@@ -133,7 +133,7 @@ def test_config3_batch_properties(ume):
     # a single pair (1024 keypoints) runs the CTA-per-keypoint moment kernel, the batch the
     # warp-per-keypoint kernel: same neighbours, different summation order
     assert np.abs(host(one["D"])[0] - D[5]).max() < 2e-3
-    # the engine's host path (chunks of 3 pairs = 3072 keypoints: the warp kernel again) returns
+    # the engine's host path (chunks of 4 pairs = 4096 keypoints: the warp kernel again) returns
     # EXACTLY what the device path returns: results are a pure function of the inputs
     T = host(out["T"]).copy()
     hostb = {k: torch.from_numpy(b[k]).pin_memory() for k in keys}

@@ -80,6 +80,7 @@ def test_reference_eval_loop_source_runs_on_the_patched_names(ume, golden, fma):
         m = host(ns["m"])[0]
         D = host(ns["D"])[0]
         F_src = host(ns["ume_src"])                                            # gathered by m[...,0] = identity
+        G_in, H_in = host(ns["G"]), host(ns["H"])                              # what batch_estimate_transform_ume_old was given
     finally:
         for k, v in saved.items():
             setattr(ev, k, v)
@@ -99,19 +100,22 @@ def test_reference_eval_loop_source_runs_on_the_patched_names(ume, golden, fma):
     err = np.abs(F_src - g["F_src"]).max(axis=(-1, -2)) / np.abs(g["F_src"]).max(axis=(-1, -2)) / kappa
     # fma=True may move a neighbour that sits within one ulp of r^2 in or out (pytorch3d CUDA vs CPU arithmetic)
     assert np.median(err) < 3e-6 and (fma or err.max() < 3e-6)
+    # the solve, judged on ITS inputs (this path's own fp32 moment matrices, gathered by evaluate.py:230-231):
+    # fp64 oracle on the same matrices; tolerance 1e-4 rad / 1e-4 m or the reference's own fp32 distance to
+    # fp64 on the same hypothesis where that is larger (absolute coordinates: SURVEY §7 "Tolerance")
+    T64, _ = orc.rigid_from_ume(G_in.astype(np.float64), H_in.astype(np.float64), dtype=np.float64)
     same = m[:, 1] == g["match"][0, :, 1]
-    G = g["F_src"][0][g["match"][0, :, 0]]
-    H = g["F_tgt"][0][g["match"][0, :, 1]]
-    T64, _ = orc.rigid_from_ume(G, H, dtype=np.float64)
-    ang = orc.rotation_angle_rad(T[same][:, :3, :3], T64[same][:, :3, :3])
-    ang_ref = orc.rotation_angle_rad(g["T"][same][:, :3, :3], T64[same][:, :3, :3])
-    terr = np.abs(T[same][:, :3, 3] - T64[same][:, :3, 3]).max(-1)
-    terr_ref = np.abs(g["T"][same][:, :3, 3] - T64[same][:, :3, 3]).max(-1)
-    if not fma:
-        assert (ang <= np.maximum(1e-4, 2 * ang_ref)).all(), (ang.max(), ang_ref.max())
-        assert (terr <= np.maximum(1e-4, 2 * terr_ref)).all(), (terr.max(), terr_ref.max())
-    else:
-        assert np.median(ang) <= max(1e-4, 2 * np.median(ang_ref)) and np.median(terr) <= max(1e-4, 2 * np.median(terr_ref))
+    Tr64, _ = orc.rigid_from_ume(g["F_src"][0][g["match"][0, :, 0]], g["F_tgt"][0][g["match"][0, :, 1]], dtype=np.float64)
+    ang = orc.rotation_angle_rad(T[:, :3, :3], T64[:, :3, :3])
+    terr = np.abs(T[:, :3, 3] - T64[:, :3, 3]).max(-1)
+    ang_ref = orc.rotation_angle_rad(g["T"][:, :3, :3], Tr64[:, :3, :3])
+    terr_ref = np.abs(g["T"][:, :3, 3] - Tr64[:, :3, 3]).max(-1)
+    assert (ang[same] <= np.maximum(1e-4, 3 * ang_ref[same])).all(), (ang.max(), ang_ref.max())
+    assert (terr[same] <= np.maximum(1e-4, 3 * terr_ref[same])).all(), (terr.max(), terr_ref.max())
+    assert np.median(ang) <= max(1e-4, 2 * np.median(ang_ref)) and np.median(terr) <= max(1e-4, 2 * np.median(terr_ref))
+    # and against the reference's golden transforms themselves where the match is the same
+    dT = np.abs(T[same] - g["T"][same]).max(axis=(-1, -2))
+    assert np.median(dT) < 1e-3, np.median(dT)
 
 
 def test_inference_kernels_refuse_inputs_that_require_grad(ume):

@@ -136,32 +136,41 @@ UME_DEVI bool point_cell(const GridHeader& h, float x, float y, float z, int* ce
 // ---------------------------------------------------------------- binning
 // A STABLE counting sort by cell: inside a cell the points keep their row order, so the sorted array —
 // and with it every sum the moment kernels form by walking it — is a pure function of the input
-// (bit-reproducible from launch to launch; the first version ranked with shared-memory atomics and
-// was not).  Each CTA owns a contiguous slice of one cloud and a shared-memory histogram:
-//   * a warp owns kRankRun * 32 CONSECUTIVE rows of every tile; equal cells inside a group of 32 are
-//     ranked with match.any (lower lane first);
-//   * the warps of a tile update the histogram one after the other, in row order (one CTA barrier per
-//     turn; the point loads and the cell arithmetic of the whole tile are done before the turns start);
-//   * the CTA's per-cell counts go to a (slice, cell) table; the scan kernel turns them into
-//     cell_start[] and, in place, into every slice's first slot inside each cell.
-// No global atomics, no memset, and the scatter pass is position = slice_base[slice][cell] + rank.
+// (bit-reproducible from launch to launch; the first version ranked with shared-memory atomics alone
+// and was not).  Each CTA owns a contiguous slice of one cloud and a shared-memory histogram:
+//   pass A  every point takes a PROVISIONAL rank inside its cell with one shared-memory atomic
+//           (fast, but the order the atomics land in is arbitrary);
+//   scan    exclusive scan of the slice's per-cell counts: the slice's points, grouped by cell, fit a
+//           shared-memory array of 16-bit slice-local row numbers (everything stays coalesced in HBM);
+//   pass B  every point drops its row number into its cell's group at its provisional rank;
+//   pass C  every point reads its group (about three members on average) and counts the members
+//           with a smaller row index: that is its STABLE rank, whatever order the atomics took.
+// The CTA's per-cell counts go to a (slice, cell) table; the scan kernel turns them into cell_start[]
+// and, in place, into every slice's first slot inside each cell.  No global atomics, no memset, and
+// the scatter pass is position = slice_base[slice][cell] + rank.
 constexpr int kRankThreads = 512;
-constexpr int kRankWarps = kRankThreads / 32;
-constexpr int kRankRun = 4;                                   // groups of 32 consecutive rows per warp and tile
-constexpr int kRankTile = kRankThreads * kRankRun;
 
 // slices per cloud: about four CTAs per SM in total, at least ~2048 rows per slice
 static int grid_slices(int B, int N) {
     int G = (4 * 148) / (B > 0 ? B : 1);
     const int cap = N / 2048 < 64 ? N / 2048 : 64;
     if (G > cap) G = cap;
+    const int need = (N + 65534) / 65535;                    // slice-local row numbers are 16 bits wide
+    if (G < need) G = need;
     return G < 1 ? 1 : G;
 }
 
 __global__ void __launch_bounds__(kRankThreads)
 grid_rank_kernel(const float* __restrict__ pts, int N, int per, const GridHeader* __restrict__ hdr,
                  int* __restrict__ slice_cnt, int cells_cap, int* __restrict__ cell_of, int* __restrict__ rank_of) {
-    extern __shared__ int s_hist[];
+    // 16-bit shared memory throughout (a slice holds < 65536 rows): cells_cap + 2 per-cell counters — bumped
+    // two to a 32-bit word by the atomics, then turned in place into exclusive starts — and `per` slots
+    // for the slice's row numbers grouped by cell.  43 KB at the usual sizes: four CTAs per SM.
+    extern __shared__ unsigned s_words[];
+    unsigned short* s_cnt = reinterpret_cast<unsigned short*>(s_words);
+    unsigned short* tmp = s_cnt + cells_cap + 2;
+    __shared__ int s_warp[kRankThreads / 32];
+    __shared__ int s_running;
     const int b = blockIdx.y, G = gridDim.x, g = blockIdx.x;
     const GridHeader h = hdr[b];
     const int ncells = h.ncells;
@@ -169,49 +178,62 @@ grid_rank_kernel(const float* __restrict__ pts, int N, int per, const GridHeader
     const float* pb = pts + (size_t)b * N * 3;
     int* cell_b = cell_of + (size_t)b * N;
     int* rank_b = rank_of + (size_t)b * N;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt = lanemask_lt();
-    for (int c = threadIdx.x; c < ncells; c += kRankThreads) s_hist[c] = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int w = tid; w <= (ncells + 1) / 2; w += kRankThreads) s_words[w] = 0u;
+    if (tid == 0) s_running = 0;
     __syncthreads();
-    for (int t0 = lo; t0 < hi; t0 += kRankTile) {
-        // this warp's rows of the tile: t0 + warp * (32 * kRankRun) + 32 r + lane
-        int cell[kRankRun], intra[kRankRun], grp[kRankRun];
-        const int w0 = t0 + warp * (32 * kRankRun);
-#pragma unroll
-        for (int r = 0; r < kRankRun; ++r) {
-            const int i = w0 + 32 * r + lane;
-            int c = -1;
-            if (i < hi) {
-                const float x = pb[(size_t)i * 3 + 0], y = pb[(size_t)i * 3 + 1], z = pb[(size_t)i * 3 + 2];
-                if (!point_cell(h, x, y, z, &c)) c = -1;
-                cell_b[i] = c;
-            }
-            cell[r] = c;
-            const unsigned peers = __match_any_sync(UME_FULL_MASK, c);
-            intra[r] = __popc(peers & lt);
-            grp[r] = (intra[r] == 0) ? __popc(peers) : 0;      // the group's first lane carries its size
-        }
-        int base[kRankRun];
-        for (int turn = 0; turn < kRankWarps; ++turn) {        // row order: warp 0's rows come first
-            if (turn == warp) {
-#pragma unroll
-                for (int r = 0; r < kRankRun; ++r) {
-                    base[r] = (cell[r] >= 0) ? s_hist[cell[r]] : 0;
-                    __syncwarp();
-                    if (cell[r] >= 0 && grp[r]) s_hist[cell[r]] = base[r] + grp[r];
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-        }
-#pragma unroll
-        for (int r = 0; r < kRankRun; ++r) {
-            const int i = w0 + 32 * r + lane;
-            if (i < hi && cell[r] >= 0) rank_b[i] = base[r] + intra[r];
+    // pass A: cell and provisional rank
+    for (int i = lo + tid; i < hi; i += kRankThreads) {
+        const float x = pb[(size_t)i * 3 + 0], y = pb[(size_t)i * 3 + 1], z = pb[(size_t)i * 3 + 2];
+        int cell;
+        if (point_cell(h, x, y, z, &cell)) {
+            cell_b[i] = cell;
+            const unsigned old = atomicAdd(&s_words[cell >> 1], (cell & 1) ? 65536u : 1u);
+            rank_b[i] = (int)((old >> (16 * (cell & 1))) & 0xffffu);
+        } else {
+            cell_b[i] = -1;
         }
     }
+    __syncthreads();
+    // the slice's per-cell counts -> global table; exclusive scan in place (s_cnt[c] = first slot of cell c)
     int* out = slice_cnt + ((size_t)b * G + g) * cells_cap;
-    for (int c = threadIdx.x; c < ncells; c += kRankThreads) out[c] = s_hist[c];
+    for (int base = 0; base <= ncells; base += kRankThreads) {
+        const int c = base + tid;
+        const int v = (c < ncells) ? (int)s_cnt[c] : 0;
+        if (c < ncells) out[c] = v;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(UME_FULL_MASK, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int k = 0; k < warp; ++k) wbase += s_warp[k];
+        const int run0 = s_running;
+        if (c <= ncells) s_cnt[c] = (unsigned short)(run0 + wbase + incl - v);
+        __syncthreads();
+        if (tid == kRankThreads - 1) s_running = run0 + wbase + incl;
+        __syncthreads();
+    }
+    // pass B: slice-local row numbers grouped by cell, in the (arbitrary) order of the provisional ranks
+    for (int i = lo + tid; i < hi; i += kRankThreads) {
+        const int c = cell_b[i];                             // written by this same thread
+        if (c >= 0) tmp[(int)s_cnt[c] + rank_b[i]] = (unsigned short)(i - lo);
+    }
+    __syncthreads();
+    // pass C: stable rank = members of the group with a smaller row number
+    for (int i = lo + tid; i < hi; i += kRankThreads) {
+        const int c = cell_b[i];
+        if (c >= 0) {
+            const int s0 = s_cnt[c], n = (int)s_cnt[c + 1] - s0;
+            const int me = i - lo;
+            int r = 0;
+            for (int k = 0; k < n; ++k) r += ((int)tmp[s0 + k] < me) ? 1 : 0;
+            rank_b[i] = r;
+        }
+    }
 }
 
 // One CTA per cloud: per-cell totals over the slices, exclusive scan over the cells in use
@@ -305,7 +327,7 @@ int grid_build(const float* pts, const float* q, int B, int N, int nq, float exp
     UME_REQUIRE(ws.ok(), UME_ERR_WORKSPACE, "grid_build: workspace too small (%zu needed, %zu given)",
                 ws.used, ws.size);
     UME_REQUIRE(B <= 65535, UME_ERR_UNSUPPORTED, "grid_build: more than 65535 clouds per call");
-    const size_t smem = (size_t)cells_cap * sizeof(int);
+    const size_t smem = (size_t)(cells_cap + 2 + per) * sizeof(unsigned short) + 16;
     cudaError_t e = cudaFuncSetAttribute(grid_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     UME_REQUIRE(e == cudaSuccess, UME_ERR_CUDA, "grid_build: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
 

@@ -174,13 +174,14 @@ __global__ void rotation_error_kernel(const float* __restrict__ R, const float* 
     if (i >= n) return;
     const float* a = R + i * sr;
     const float* b = Rh + i * sh;
+    const int la = (sr >= 12) ? 4 : 3, lb = (sh >= 12) ? 4 : 3;   // row pitch: 3 (packed 3x3) or 4 (block of a 4x4 transform)
     // trace(R_hat R^T) = sum_jk R_hat[j][k] R[j][k]   (the einsum of :66-67 after the matmul of :65)
     float tr = 0.f;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         float row = 0.f;                                   // (R_hat R^T)[j][j], a 3-term dot as torch.matmul forms it
 #pragma unroll
-        for (int k = 0; k < 3; ++k) row = fmaf(b[j * 3 + k], a[j * 3 + k], row);
+        for (int k = 0; k < 3; ++k) row = fmaf(b[j * lb + k], a[j * la + k], row);
         tr += row;
     }
     tr = fminf(fmaxf(tr, -1.f), 3.f);
@@ -197,7 +198,8 @@ extern "C" int ume_rotation_error_deg_f32(const float* R, const float* R_hat, in
     UME_REQUIRE(n >= 0, UME_ERR_BAD_ARG, "ume_rotation_error_deg_f32: negative size");
     if (n == 0) return UME_OK;
     UME_REQUIRE(R && R_hat && out, UME_ERR_BAD_ARG, "ume_rotation_error_deg_f32: null pointer");
-    UME_REQUIRE(stride_R >= 9 && stride_R_hat >= 9, UME_ERR_BAD_ARG, "ume_rotation_error_deg_f32: stride < 9");
+    UME_REQUIRE((stride_R == 9 || stride_R == 16) && (stride_R_hat == 9 || stride_R_hat == 16), UME_ERR_BAD_ARG,
+                "ume_rotation_error_deg_f32: stride must be 9 (packed 3x3) or 16 (4x4 transforms)");
     UME_REQUIRE((n + 255) / 256 < 0x7fffffffll, UME_ERR_UNSUPPORTED, "ume_rotation_error_deg_f32: too many rotations");
     rotation_error_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(R, R_hat, n, stride_R, stride_R_hat, out);
     count_launch();
