@@ -50,6 +50,8 @@ typedef enum ume_status {
                                       for C in {16,32,64,128} and B*n >= 3072 keypoints is the
                                       warp-per-keypoint kernel)                                      */
 #define UME_FLAG_WARP_MOMENTS  16u /* ume_moments_f32: warp-per-keypoint kernel also for small launches */
+#define UME_FLAG_CORR_THREAD   32u /* ume_corr_scores_f32: the round-1 thread-per-query kernel instead of the tile
+                                      kernel (kept for comparison; same results up to summation order)     */
 
 int ume_abi_version(void);
 const char* ume_last_error(void);
@@ -111,6 +113,12 @@ int ume_neighbor_count_f32(const float* pts, const float* kpts, int B, int N, in
  * (all-zero input gives e0..e3, like LAPACK); `rank` (nmat) int32 may be NULL. */
 int ume_orthonormalize_f32(const float* F, int64_t nmat, int C, float* Qt, int32_t* rank, void* stream);
 
+/* Same, additionally (or only: Qt may be NULL) emitting the distance kernel's tensor-core operand
+ *   Qh (nmat, 4, 2C) __half: row = [hi (C) | lo (C)], hi = fp16(256 q), lo = fp16(256 q - hi)
+ * (see ume_cdist_split_f16).  The fused pipeline uses this to skip the split pre-pass. */
+int ume_orthonormalize_split_f32(const float* F, int64_t nmat, int C, float* Qt, void* Qh, int32_t* rank,
+                                 void* stream);
+
 /* ---------------------------------------------------------------- all-pairs subspace distance
  * Replaces utils/loc_utils.py:12-13 (P = QQ^T, torch.cdist(P1.flatten, P2.flatten)/sqrt 2) and the
  * arg-min of evaluate.py:224 through the identity D^2 = 4 - |Q1^T Q2|_F^2.
@@ -118,11 +126,17 @@ int ume_orthonormalize_f32(const float* F, int64_t nmat, int C, float* Qt, int32
  *   D      (B,n1,n2) (may be NULL)
  *   argmin (B,n1) int64 = first index of the row minimum (may be NULL)
  *   dmin   (B,n1) the row minimum (may be NULL)
- * `impl`: 0 = fp32 SIMT kernel, 1 = tcgen05 tensor-core kernel (3xTF32 split, fp32-grade).
+ * `impl`: 0 = fp32 SIMT kernel, 1 = tcgen05 tensor-core kernel (operands split into two FP16 numbers,
+ *         three kind::f16 products per term: fp32-grade; descriptor entries must satisfy |q| < 255).
  * Limits: C multiple of 4, C <= 128. */
 size_t ume_cdist_workspace_bytes(int B, int n1, int n2, int C, int impl);
 int ume_cdist_f32(const float* Qt1, const float* Qt2, int B, int n1, int n2, int C, int impl, float* D,
                   int64_t* argmin, float* dmin, void* ws, size_t ws_bytes, void* stream);
+
+/* The tensor-core distance kernel on pre-split operands (ume_orthonormalize_split_f32's Qh):
+ *   Qh1 (B,n1,4,2C), Qh2 (B,n2,4,2C) __half.  Same outputs as ume_cdist_f32; no workspace.  C = 32 or 64. */
+int ume_cdist_split_f16(const void* Qh1, const void* Qh2, int B, int n1, int n2, int C, float* D, int64_t* argmin,
+                        float* dmin, void* stream);
 
 /* Distance between CORRESPONDING descriptors: Dp[i] = scale * sqrt(8 - 2 |Q1_i^T Q2_i|_F^2).
  * utils/loc_utils.py:344 uses scale = 0.707 (literally), ume_cdist uses 1/sqrt(2). */
@@ -203,6 +217,12 @@ size_t ume_corr_scores_workspace_bytes(int Ns, int Nt, int n_hyp);
 int ume_corr_scores_f32(const float* src_pts, const float* tgt_pts, const float* wf_src, const float* wf_tgt,
                         const float* T, int Ns, int Nt, int C, int n_hyp, int K, float sigma, unsigned flags,
                         float* score, int64_t* best, void* ws, size_t ws_bytes, void* stream);
+
+/* Diagnostics of the tile kernel behind ume_corr_scores_f32 (off by default, not on the measured path):
+ * enable != 0 switches the counters on; out8_host (may be NULL) receives, then resets, {queries served by
+ * the tile path, by the ring-search fallback, staged candidates, (tile, hypothesis) items, items whose
+ * block did not fit, items with fewer than K candidates, 0, 0}.  Synchronises the device. */
+int ume_corr_stats(int enable, uint64_t* out8_host);
 
 /* ---------------------------------------------------------------- voxel de-duplication
  * Replaces MinkowskiEngine `ME.utils.sparse_quantize(coordinates, return_index=True, quantization_size=q)`

@@ -8,7 +8,7 @@ See DESIGN.md for the path and its boundary, include/umereg_b200.h for the C ABI
 """
 from .api import (ball_query, knn_points, knn_gather, knn1_transfer, ume_moments, ume_moments_backward,
                   neighbor_count, my_ume_generation,
-                  create_local_ume_matrix, ume_descriptors, descriptor_cdist, ume_cdist, rigid_solve,
+                  create_local_ume_matrix, ume_descriptors, ume_descriptors_split, descriptor_cdist, descriptor_cdist_split, ume_cdist, rigid_solve,
                   batch_estimate_transform_ume_old, relative_rotation_error, ball_query_gather, ume_kp_layer,
                   register_hypotheses, feature_spatial_var, cauchy_kernel, correlation_scores,
                   pc_corr_cost_pytorch3d, weighted_features, FeatureCorrelator, weighted_match_subsample, sparse_quantize,
@@ -17,7 +17,7 @@ from .patch import patch_reference
 
 __all__ = ["ball_query", "knn_points", "knn_gather", "knn1_transfer", "ume_moments", "ume_moments_backward",
            "neighbor_count", "my_ume_generation",
-           "create_local_ume_matrix", "ume_descriptors", "descriptor_cdist", "ume_cdist", "rigid_solve",
+           "create_local_ume_matrix", "ume_descriptors", "ume_descriptors_split", "descriptor_cdist", "descriptor_cdist_split", "ume_cdist", "rigid_solve",
            "batch_estimate_transform_ume_old", "relative_rotation_error", "ball_query_gather", "ume_kp_layer",
            "register_hypotheses", "feature_spatial_var", "cauchy_kernel", "correlation_scores",
            "pc_corr_cost_pytorch3d", "weighted_features", "FeatureCorrelator", "weighted_match_subsample",

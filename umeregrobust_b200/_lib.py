@@ -22,6 +22,7 @@ UME_FLAG_CELL_DIV2 = 2
 UME_FLAG_CTA_MOMENTS = 4
 UME_FLAG_RAW_MOMENTS = 8
 UME_FLAG_WARP_MOMENTS = 16
+UME_FLAG_CORR_THREAD = 32
 
 _lock = threading.Lock()
 _lib = None
@@ -90,6 +91,8 @@ def _bind(lib):
         "ume_moments_backward_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, u32, vp, vp, sz, vp]),
         "ume_neighbor_count_f32": (i32, [vp, vp, i32, i32, i32, i32, f32, u32, vp, vp, sz, vp]),
         "ume_orthonormalize_f32": (i32, [vp, i64, i32, vp, vp, vp]),
+        "ume_orthonormalize_split_f32": (i32, [vp, i64, i32, vp, vp, vp, vp]),
+        "ume_cdist_split_f16": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
         "ume_cdist_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
         "ume_cdist_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]),
         "ume_pair_dist_f32": (i32, [vp, vp, i64, i32, f32, vp, vp]),
@@ -106,6 +109,7 @@ def _bind(lib):
         "ume_linear_sum_assignment_host_f32": (i32, [vp, i32, i32, vp, vp]),
         "ume_voxel_unique_workspace_bytes": (sz, [i32]),
         "ume_voxel_unique_f32": (i32, [vp, i32, f32, vp, vp, vp, vp, sz, vp]),
+        "ume_corr_stats": (i32, [i32, vp]),
         "ume_corr_scores_workspace_bytes": (sz, [i32, i32, i32]),
         "ume_corr_scores_f32": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, u32, vp, vp, vp, sz, vp]),
     }
@@ -126,7 +130,7 @@ EXPORTED_SYMBOLS = ["ume_abi_version", "ume_last_error", "ume_status_string", "u
                     "ume_corr_scores_workspace_bytes", "ume_corr_scores_f32",
                     "ume_voxel_unique_workspace_bytes", "ume_voxel_unique_f32",
                     "ume_moments_backward_f32", "ume_neighbor_count_f32", "ume_linear_sum_assignment_host_f32",
-                    "ume_rotation_error_deg_f32", "ume_gumbel_topk_f32"]
+                    "ume_rotation_error_deg_f32", "ume_gumbel_topk_f32", "ume_orthonormalize_split_f32", "ume_cdist_split_f16", "ume_corr_stats"]
 
 
 def lib():

@@ -24,7 +24,9 @@ _KNN = collections.namedtuple("_KNN", ["dists", "idx", "knn"])
 #              (default: warp kernel for C in {16,32,64,128} and launches of >= 3072 keypoints)
 #   cdist_impl: 0 = fp32 SIMT distance kernel, 1 = tcgen05 tensor-core kernel
 #               (C = 32 / 64 only), None = tensor cores whenever the channel count allows
-config = {"fma_dist": False, "cell_div2": False, "cdist_impl": None, "cta_moments": False, "warp_moments": False}
+#   corr_thread: hypothesis scoring with the round-1 thread-per-query kernel instead of the tile kernel
+config = {"fma_dist": False, "cell_div2": False, "cdist_impl": None, "cta_moments": False, "warp_moments": False,
+          "corr_thread": False}
 
 _workspaces = {}
 _workspaces_lock = threading.Lock()
@@ -33,7 +35,8 @@ _workspaces_lock = threading.Lock()
 def _flags():
     return ((_lib.UME_FLAG_FMA_DIST if config["fma_dist"] else 0) | (_lib.UME_FLAG_CELL_DIV2 if config["cell_div2"] else 0)
             | (_lib.UME_FLAG_CTA_MOMENTS if config["cta_moments"] is True else 0)
-            | (_lib.UME_FLAG_WARP_MOMENTS if config["cta_moments"] is False and config.get("warp_moments") else 0))
+            | (_lib.UME_FLAG_WARP_MOMENTS if config["cta_moments"] is False and config.get("warp_moments") else 0)
+            | (_lib.UME_FLAG_CORR_THREAD if config.get("corr_thread") else 0))
 
 
 def _stream():
@@ -304,6 +307,43 @@ def ume_descriptors(ume, return_rank=False, buf=None, tag=""):
         rc = _lib.lib().ume_orthonormalize_f32(_ptr(ume), nmat, C, _ptr(Qt), _ptr(rank), _stream())
     _lib.check(rc, "ume_descriptors")
     return (Qt, rank) if return_rank else Qt
+
+
+def ume_descriptors_split(ume, buf=None, tag="", want_Qt=False):
+    """Orthonormal bases as the tensor-core distance kernel's operand: Qh (..., 4, 2C) float16, rows
+    [hi | lo] of 256 q (`ume_orthonormalize_split_f32`), optionally with the fp32 Qt as well.  Feeding
+    `descriptor_cdist_split` with these skips the split pre-pass of the generic `descriptor_cdist`."""
+    ume = _dev_f32(ume, "ume")
+    if ume.dim() < 2 or ume.shape[-1] != 4:
+        raise ValueError("ume_descriptors_split: expected (..., C, 4), got %s" % (tuple(ume.shape),))
+    C = ume.shape[-2]
+    nmat = ume.numel() // (C * 4) if C > 0 else 0
+    Qh = _out(buf, "Qh" + tag, tuple(ume.shape[:-2]) + (4, 2 * C), torch.float16, ume.device)
+    Qt = _out(buf, "Qt" + tag, tuple(ume.shape[:-2]) + (4, C), torch.float32, ume.device) if want_Qt else None
+    with torch.cuda.device(ume.device):
+        rc = _lib.lib().ume_orthonormalize_split_f32(_ptr(ume), nmat, C, _ptr(Qt), _ptr(Qh), None, _stream())
+    _lib.check(rc, "ume_descriptors_split")
+    return (Qh, Qt) if want_Qt else Qh
+
+
+def descriptor_cdist_split(Qh1, Qh2, want_D=True, want_argmin=False, buf=None):
+    """`descriptor_cdist` on pre-split float16 operands (B,n,4,2C) from `ume_descriptors_split`: the
+    tcgen05 kernel without its split pre-pass and without a workspace.  C = 32 or 64."""
+    if Qh1.dtype != torch.float16 or Qh2.dtype != torch.float16 or not Qh1.is_cuda or Qh1.dim() != 4 or Qh2.dim() != 4:
+        raise ValueError("descriptor_cdist_split: expected float16 CUDA tensors (B,n,4,2C)")
+    Qh1, Qh2 = Qh1.contiguous(), Qh2.contiguous()
+    B, n1, _, C2 = Qh1.shape
+    n2 = Qh2.shape[1]
+    if Qh2.shape[0] != B or Qh2.shape[3] != C2 or Qh1.shape[2] != 4 or Qh2.shape[2] != 4:
+        raise ValueError("descriptor_cdist_split: shapes %s and %s do not agree" % (tuple(Qh1.shape), tuple(Qh2.shape)))
+    dev = Qh1.device
+    D = _out(buf, "D", (B, n1, n2), torch.float32, dev) if want_D else None
+    am = _out(buf, "argmin", (B, n1), torch.int64, dev) if want_argmin else None
+    dm = _out(buf, "dmin", (B, n1), torch.float32, dev) if want_argmin else None
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ume_cdist_split_f16(_ptr(Qh1), _ptr(Qh2), B, n1, n2, C2 // 2, _ptr(D), _ptr(am), _ptr(dm), _stream())
+    _lib.check(rc, "descriptor_cdist_split")
+    return D, am, dm
 
 
 def descriptor_cdist(Qt1, Qt2, want_D=True, want_argmin=False, impl=None, buf=None):
@@ -737,8 +777,14 @@ def register_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K,
         A, Bm = F_src, F_tgt
     if matching not in ("argmin", "hungarian"):
         raise ValueError("register_hypotheses: matching must be 'argmin' or 'hungarian'")
-    D, am, dm = descriptor_cdist(ume_descriptors(A, buf=buf, tag="_src"), ume_descriptors(Bm, buf=buf, tag="_tgt"),
-                                 want_D=want_D or matching == "hungarian", want_argmin=True, buf=buf)
+    C = A.shape[-2]
+    if C in (32, 64) and config["cdist_impl"] in (None, 1):
+        # tensor-core distance kernel, operands written pre-split by the orthonormalisation kernel
+        D, am, dm = descriptor_cdist_split(ume_descriptors_split(A, buf=buf, tag="_src"), ume_descriptors_split(Bm, buf=buf, tag="_tgt"),
+                                           want_D=want_D or matching == "hungarian", want_argmin=True, buf=buf)
+    else:
+        D, am, dm = descriptor_cdist(ume_descriptors(A, buf=buf, tag="_src"), ume_descriptors(Bm, buf=buf, tag="_tgt"),
+                                     want_D=want_D or matching == "hungarian", want_argmin=True, buf=buf)
     if matching == "hungarian":
         m = hungarian_match(D)
         gi, hi = m[..., 0].contiguous(), m[..., 1].contiguous()

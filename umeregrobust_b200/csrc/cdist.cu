@@ -10,6 +10,8 @@ namespace ume {
 int cdist_tc_launch(const float* Qt1, const float* Qt2, int B, int n1, int n2, int C, float* D, int64_t* argmin,
                     float* dmin, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t cdist_tc_workspace_bytes(int B, int n1, int n2, int C);
+int cdist_tc_launch_split(const void* Qh1, const void* Qh2, int B, int n1, int n2, int C, float* D, int64_t* argmin,
+                          float* dmin, cudaStream_t stream);
 
 namespace {
 
@@ -148,4 +150,17 @@ extern "C" int ume_cdist_f32(const float* Qt1, const float* Qt2, int B, int n1, 
     cdist_simt_kernel<<<grid, 256, smem, stream>>>(Qt1, Qt2, n1, n2, C, D, argmin, dmin);
     count_launch();
     return check_launch("cdist_simt_kernel");
+}
+
+extern "C" int ume_cdist_split_f16(const void* Qh1, const void* Qh2, int B, int n1, int n2, int C, float* D, int64_t* argmin,
+                                   float* dmin, void* stream_) {
+    using namespace ume;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    UME_REQUIRE(B >= 0 && n1 >= 0 && n2 >= 0, UME_ERR_BAD_ARG, "ume_cdist_split_f16: negative size");
+    if (B == 0 || n1 == 0) return UME_OK;
+    UME_REQUIRE(n2 >= 1 || (!argmin && !dmin), UME_ERR_BAD_ARG, "ume_cdist_split_f16: arg-min over an empty row (n2 = 0)");
+    if (n2 == 0) return UME_OK;
+    UME_REQUIRE(Qh1 && Qh2, UME_ERR_BAD_ARG, "ume_cdist_split_f16: null pointer");
+    UME_REQUIRE(B <= 65535, UME_ERR_UNSUPPORTED, "ume_cdist_split_f16: B = %d > 65535", B);
+    return cdist_tc_launch_split(Qh1, Qh2, B, n1, n2, C, D, argmin, dmin, stream);
 }

@@ -9,6 +9,8 @@
 // Output is written transposed, (4, C): the K-major operand of the distance GEMM.
 #include "ume_common.cuh"
 
+#include <cuda_fp16.h>
+
 namespace ume {
 namespace {
 
@@ -22,7 +24,8 @@ UME_DEVI float warp_sum(float v) {
 
 template <int RPL>
 __global__ void __launch_bounds__(256) ortho_kernel(const float* __restrict__ F, int64_t nmat, int C,
-                                                    float* __restrict__ Qt, int32_t* __restrict__ rank_out) {
+                                                    float* __restrict__ Qt, __half* __restrict__ Qh,
+                                                    int32_t* __restrict__ rank_out) {
     const int lane = threadIdx.x & 31;
     const int64_t mat = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (mat >= nmat) return;
@@ -121,13 +124,33 @@ __global__ void __launch_bounds__(256) ortho_kernel(const float* __restrict__ F,
 #pragma unroll
         for (int r = 0; r < RPL; ++r) q[r][j] = v[r] * inv1;
     }
-    float* Qm = Qt + mat * 4 * C;
+    if (Qt) {
+        float* Qm = Qt + mat * 4 * C;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 4; ++j) {
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) {
-            const int c = lane + 32 * r;
-            if (c < C) Qm[(size_t)j * C + c] = q[r][j];
+            for (int r = 0; r < RPL; ++r) {
+                const int c = lane + 32 * r;
+                if (c < C) Qm[(size_t)j * C + c] = q[r][j];
+            }
+        }
+    }
+    if (Qh) {
+        // the distance GEMM's operand (cdist_tc.cu): row j = [hi (C) | lo (C)] halves of 256 q, written here so
+        // that no separate split pass (an extra read and write of the descriptors) is needed
+        __half* Hm = Qh + mat * 4 * 2 * C;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const int c = lane + 32 * r;
+                if (c < C) {
+                    const float v = q[r][j] * 256.f;
+                    const __half hi = __float2half_rn(v);
+                    Hm[(size_t)j * 2 * C + c] = hi;
+                    Hm[(size_t)j * 2 * C + C + c] = __float2half_rn(v - __half2float(hi));
+                }
+            }
         }
     }
     if (rank_out && lane == 0) rank_out[mat] = rank;
@@ -169,26 +192,38 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const float* __restrict_
 }  // namespace
 }  // namespace ume
 
-extern "C" int ume_orthonormalize_f32(const float* F, int64_t nmat, int C, float* Qt, int32_t* rank, void* stream_) {
+static int orthonormalize(const float* F, int64_t nmat, int C, float* Qt, void* Qh, int32_t* rank, void* stream_,
+                         const char* who) {
     using namespace ume;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    UME_REQUIRE(nmat >= 0, UME_ERR_BAD_ARG, "ume_orthonormalize_f32: negative nmat");
+    UME_REQUIRE(nmat >= 0, UME_ERR_BAD_ARG, "%s: negative nmat", who);
     if (nmat == 0) return UME_OK;
-    UME_REQUIRE(F && Qt, UME_ERR_BAD_ARG, "ume_orthonormalize_f32: null pointer");
+    UME_REQUIRE(F && (Qt || Qh), UME_ERR_BAD_ARG, "%s: null pointer", who);
     UME_REQUIRE(C >= 4 && C <= 32 * kMaxRowsPerLane, UME_ERR_UNSUPPORTED,
-                "ume_orthonormalize_f32: C = %d not in [4,256] (a C x 4 matrix needs C >= 4 for a rank-4 basis)", C);
-    UME_REQUIRE(reinterpret_cast<uintptr_t>(F) % 16 == 0, UME_ERR_BAD_ARG, "ume_orthonormalize_f32: F not 16-byte aligned");
+                "%s: C = %d not in [4,256] (a C x 4 matrix needs C >= 4 for a rank-4 basis)", who, C);
+    UME_REQUIRE(reinterpret_cast<uintptr_t>(F) % 16 == 0, UME_ERR_BAD_ARG, "%s: F not 16-byte aligned", who);
     const int wpb = 8;
     const int64_t blocks = (nmat + wpb - 1) / wpb;
-    UME_REQUIRE(blocks < 0x7fffffffll, UME_ERR_UNSUPPORTED, "ume_orthonormalize_f32: too many matrices");
+    UME_REQUIRE(blocks < 0x7fffffffll, UME_ERR_UNSUPPORTED, "%s: too many matrices", who);
     const int rpl = (C + 31) / 32;
+    __half* H = static_cast<__half*>(Qh);
     ProfScope prof(UME_PROF_ORTHO, stream);
-    if (rpl == 1) ortho_kernel<1><<<(unsigned)blocks, wpb * 32, 0, stream>>>(F, nmat, C, Qt, rank);
-    else if (rpl == 2) ortho_kernel<2><<<(unsigned)blocks, wpb * 32, 0, stream>>>(F, nmat, C, Qt, rank);
-    else if (rpl <= 4) ortho_kernel<4><<<(unsigned)blocks, wpb * 32, 0, stream>>>(F, nmat, C, Qt, rank);
-    else ortho_kernel<8><<<(unsigned)blocks, wpb * 32, 0, stream>>>(F, nmat, C, Qt, rank);
+    if (rpl == 1) ortho_kernel<1><<<(unsigned)blocks, wpb * 32, 0, stream>>>(F, nmat, C, Qt, H, rank);
+    else if (rpl == 2) ortho_kernel<2><<<(unsigned)blocks, wpb * 32, 0, stream>>>(F, nmat, C, Qt, H, rank);
+    else if (rpl <= 4) ortho_kernel<4><<<(unsigned)blocks, wpb * 32, 0, stream>>>(F, nmat, C, Qt, H, rank);
+    else ortho_kernel<8><<<(unsigned)blocks, wpb * 32, 0, stream>>>(F, nmat, C, Qt, H, rank);
     count_launch();
     return check_launch("ortho_kernel");
+}
+
+extern "C" int ume_orthonormalize_f32(const float* F, int64_t nmat, int C, float* Qt, int32_t* rank, void* stream) {
+    UME_REQUIRE(Qt || nmat == 0, UME_ERR_BAD_ARG, "ume_orthonormalize_f32: null pointer");
+    return orthonormalize(F, nmat, C, Qt, nullptr, rank, stream, "ume_orthonormalize_f32");
+}
+
+extern "C" int ume_orthonormalize_split_f32(const float* F, int64_t nmat, int C, float* Qt, void* Qh, int32_t* rank,
+                                            void* stream) {
+    return orthonormalize(F, nmat, C, Qt, Qh, rank, stream, "ume_orthonormalize_split_f32");
 }
 
 extern "C" int ume_pair_dist_f32(const float* Qt1, const float* Qt2, int64_t nmat, int C, float scale, float* Dp,
