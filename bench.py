@@ -54,7 +54,7 @@ WORKLOADS = {
     "nuscenes_b512_n1024_c32": dict(pairs=512, N=35000, n_kp=1024, C=32, model="NUSCENES", scaling="strong", micro=64, pool=4),
     "rotkitti_b32_n2048_c64": dict(pairs=32, N=120000, n_kp=2048, C=64, model="KITTI", scaling="weak", micro=32),
     "rotkitti_stream4096_n2048_c64": dict(pairs=4096, N=120000, n_kp=2048, C=64, model="KITTI", scaling="strong",
-                                          micro=16, stream=True, pool=4, gt="rotkitti"),
+                                          micro=16, stream=True, pool=2, gt="rotkitti"),
     "tiny": dict(pairs=4, N=20000, n_kp=256, C=32, model="KITTI", scaling="weak", micro=4),
     "tiny_stream": dict(pairs=16, N=20000, n_kp=256, C=32, model="KITTI", scaling="strong", micro=2, stream=True,
                         pool=2, gt="rotkitti"),

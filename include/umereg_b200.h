@@ -50,8 +50,6 @@ typedef enum ume_status {
                                       for C in {16,32,64,128} and B*n >= 3072 keypoints is the
                                       warp-per-keypoint kernel)                                      */
 #define UME_FLAG_WARP_MOMENTS  16u /* ume_moments_f32: warp-per-keypoint kernel also for small launches */
-#define UME_FLAG_CORR_THREAD   32u /* ume_corr_scores_f32: the round-1 thread-per-query kernel instead of the tile
-                                      kernel (kept for comparison; same results up to summation order)     */
 
 int ume_abi_version(void);
 const char* ume_last_error(void);
@@ -157,6 +155,25 @@ int ume_rigid_solve_f32(const float* G, const float* H, const int64_t* gi, const
                         const float* offG, const float* offH, int B, int nG, int nH, int nm, int C,
                         float* T, void* stream);
 
+/* ---------------------------------------------------------------- backward kernels of the training row
+ * loss.py:137-190 (`CubeRegistrationLoss`) differentiates through batch_estimate_transform_ume_old
+ * (utils/loc_utils.py:292-335): gradient of the solve above for the pairing G[i] <-> H[i].
+ *   G, H (nb,C,4), gT (nb,4,4) gradient wrt T (only T[:3,:] matters) -> gG, gH (nb,C,4).
+ * Closed form through the proper singular frames of the 3x3 cross moment (no 1/(s_i^2 - s_j^2) terms). */
+int ume_rigid_solve_backward_f32(const float* G, const float* H, const float* gT, int64_t nb, int C, float* gG,
+                                 float* gH, void* stream);
+
+/* loss.py:84-118 (`UMEContrastiveLoss`) differentiates through ume_cdist (utils/loc_utils.py:8-15: thin QR ->
+ * P = Q Q^T -> cdist / sqrt 2): gradient of D (B,n1,n2) wrt the UME matrices, closed form on the 4x4 Gram
+ * blocks (no (B,n,C,C) projector, no QR autograd).
+ *   F1 (B,n1,C,4), F2 (B,n2,C,4) full-rank UME matrices; Qt1 (B,n1,4,C), Qt2 (B,n2,4,C) their bases from
+ *   ume_orthonormalize_f32; D, gD (B,n1,n2) the forward's distances and their gradient -> gF1, gF2.
+ * Entries with D = 0 contribute nothing (as torch.cdist's backward).  4 <= C <= 128. */
+size_t ume_cdist_backward_workspace_bytes(int B, int n1, int n2, int C);
+int ume_cdist_backward_f32(const float* F1, const float* F2, const float* Qt1, const float* Qt2, const float* D,
+                           const float* gD, int B, int n1, int n2, int C, float* gF1, float* gF2, void* ws,
+                           size_t ws_bytes, void* stream);
+
 /* Replaces utils/eval_utils.py:60-76 `relative_rotation_error(R, R_hat)`:
  *   out[i] = acos((clamp(trace(R_hat_i R_i^T), -1, 3) - 1) / 2) * 180 / pi   (degrees)
  * R, R_hat: rotation matrices, row-major, `stride` floats apart: 9 = packed (n,3,3) arrays (row pitch 3),
@@ -217,12 +234,6 @@ size_t ume_corr_scores_workspace_bytes(int Ns, int Nt, int n_hyp);
 int ume_corr_scores_f32(const float* src_pts, const float* tgt_pts, const float* wf_src, const float* wf_tgt,
                         const float* T, int Ns, int Nt, int C, int n_hyp, int K, float sigma, unsigned flags,
                         float* score, int64_t* best, void* ws, size_t ws_bytes, void* stream);
-
-/* Diagnostics of the tile kernel behind ume_corr_scores_f32 (off by default, not on the measured path):
- * enable != 0 switches the counters on; out8_host (may be NULL) receives, then resets, {queries served by
- * the tile path, by the ring-search fallback, staged candidates, (tile, hypothesis) items, items whose
- * block did not fit, items with fewer than K candidates, 0, 0}.  Synchronises the device. */
-int ume_corr_stats(int enable, uint64_t* out8_host);
 
 /* ---------------------------------------------------------------- voxel de-duplication
  * Replaces MinkowskiEngine `ME.utils.sparse_quantize(coordinates, return_index=True, quantization_size=q)`

@@ -390,60 +390,3 @@ def test_cdist_presplit_operands_equal_the_generic_entry(ume, C, B, n1, n2):
     q = host(Qt1).astype(np.float64) * 256.0
     h = host(Qh1).astype(np.float64)
     assert np.abs(h[..., :C] + h[..., C:] - q).max() < 256.0 * 2.0 ** -21
-
-
-# ----------------------------------------------------------------------------- tile correlator (f1)
-def _scores_both(ume, sp, tp, sf, tf, T, k, sigma):
-    ume.config["corr_thread"] = True
-    try:
-        s_thr, b_thr = ume.correlation_scores(sp, tp, sf, tf, T, k=k, sigma=sigma)
-    finally:
-        ume.config["corr_thread"] = False
-    s_tile, b_tile = ume.correlation_scores(sp, tp, sf, tf, T, k=k, sigma=sigma)
-    return host(s_thr), int(b_thr), host(s_tile), int(b_tile)
-
-
-@pytest.mark.parametrize("Ns,Nt,C,K,n_hyp", [(1500, 1400, 32, 20, 24), (3000, 2500, 64, 20, 40), (2000, 300, 32, 8, 16),
-                                             (700, 5000, 32, 32, 12), (5000, 5000, 32, 20, 64)])
-def test_tile_correlator_equals_ring_search_kernel(ume, Ns, Nt, C, K, n_hyp):
-    """The tile kernel (staged candidates + histogram select) against the exact per-thread ring search on
-    good hypotheses, slightly wrong ones and garbage (far-away landing zones: the fallback path), small
-    target clouds (the whole cloud fits one block), K = 8 / 20 / 32, C = 32 / 64: the same K neighbours
-    for every query, hence the same scores up to the order of the fp32 sums."""
-    rng = np.random.default_rng(Ns + Nt)
-    src = np.stack([rng.uniform(-25, 25, Ns), rng.uniform(-25, 25, Ns), rng.uniform(-1.5, 2.5, Ns)], 1).astype(np.float32)
-    src[: Ns // 3, :2] *= 0.25                                             # a dense core, like a LiDAR sweep
-    gt = synth.random_rigid(rng, t_range=(2.0, 6.0))
-    sub = rng.integers(0, Ns, Nt)
-    tgt = ((src[sub] + rng.normal(scale=0.05, size=(Nt, 3))).astype(np.float64) @ gt[:3, :3].T + gt[:3, 3]).astype(np.float32)
-    tgt[:5] = tgt[5:10]                                                    # exact duplicates: ties in distance
-    W = rng.normal(size=(3, C)) * 0.2
-    sf = (np.sin(src @ W) * rng.uniform(0.5, 1.5, (Ns, 1))).astype(np.float32)
-    tf = (np.sin((tgt - gt[:3, 3]) @ gt[:3, :3] @ W)).astype(np.float32)
-    hyps = [gt]
-    for i in range(n_hyp // 2 - 1):
-        d = synth.random_rigid(rng, t_range=(0.0, 0.4 * (i + 1)), max_tilt_deg=1.0, yaw_deg=rng.uniform(-2, 2) * (i + 1))
-        hyps.append(d @ gt)
-    while len(hyps) < n_hyp:                                               # garbage, tilted out of the plane and far away
-        hyps.append(synth.random_rigid(rng, t_range=(0.0, 80.0), max_tilt_deg=60.0))
-    T = dev(np.stack(hyps).astype(np.float32))
-    s_thr, b_thr, s_tile, b_tile = _scores_both(ume, dev(src), dev(tgt), dev(sf), dev(tf), T, K, 1.5)
-    scale = np.abs(s_thr).max()
-    assert np.abs(s_tile - s_thr).max() < 2e-5 * scale, (np.abs(s_tile - s_thr).max(), scale)
-    assert b_tile == b_thr == 0
-    # bit-reproducible
-    s2 = host(ume.correlation_scores(dev(src), dev(tgt), dev(sf), dev(tf), T, k=K, sigma=1.5)[0])
-    assert np.array_equal(s2, s_tile)
-
-
-def test_tile_correlator_against_reference_golden(ume, golden):
-    g = golden("correlator")
-    sw = ume.feature_spatial_var(dev(g["src_pts"][None]), dev(g["src_feat"][None]), knn=50)[0]
-    tw = ume.feature_spatial_var(dev(g["tgt_pts"][None]), dev(g["tgt_feat"][None]), knn=50)[0]
-    m = torch.mean(torch.cat((dev(g["src_feat"]), dev(g["tgt_feat"])), 0), 0)
-    wsf = ume.weighted_features(dev(g["src_feat"]), m, sw)
-    wtf = ume.weighted_features(dev(g["tgt_feat"]), m, tw)
-    sc, best = ume.correlation_scores(dev(g["src_pts"]), dev(g["tgt_pts"]), wsf, wtf, dev(g["T_kp"]), k=int(g["corr_num_nn"]),
-                                      sigma=float(g["sigma"]))
-    assert np.abs(host(sc) - g["scores"]).max() < 1e-4 * np.abs(g["scores"]).max()
-    assert int(best) == int(np.argmax(g["scores"]))

@@ -108,3 +108,92 @@ def test_ume_losses_against_reference_golden(ume, golden):
     (ume_loss + reg_loss).backward()
     assert close(host(vf.grad), g["loss_grad_velo_feat"], 5e-3)
     assert close(host(rf.grad), g["loss_grad_ref_feat"], 5e-3)
+
+
+# ----------------------------------------------------------------------------- hand-written backward kernels
+def _torch_ume_cdist(ume1, ume2):
+    """utils/loc_utils.py:8-15 as plain differentiable torch ops (the floating-point reference of the kernels)."""
+    Q1 = torch.linalg.qr(ume1, mode="reduced").Q
+    Q2 = torch.linalg.qr(ume2, mode="reduced").Q
+    P1, P2 = Q1 @ Q1.transpose(-1, -2), Q2 @ Q2.transpose(-1, -2)
+    return torch.cdist(P1.flatten(2), P2.flatten(2)) / np.sqrt(2)
+
+
+def _torch_rigid_from_ume(G, H):
+    """The (R,t) part of utils/loc_utils.py:292-335 as plain differentiable torch ops."""
+    mg, mh, g, h = G[:, :, :1], H[:, :, :1], G[:, :, 1:], H[:, :, 1:]
+    wl = (g * mg).sum(1, keepdim=True) / ((mg * mg).sum(1, keepdim=True) + 2e-16)
+    wr = (h * mg).sum(1, keepdim=True) / ((mg * mh).sum(1, keepdim=True) + 1e-16)
+    left, right = g - wl * mg, h - wr * mh
+    U, _, Vh = torch.linalg.svd(left.transpose(1, 2) @ right)
+    fix = torch.ones(G.shape[0], 3, device=G.device, dtype=G.dtype)
+    fix[:, 2] = torch.sign(torch.det(U @ Vh))
+    R = (U * fix[:, None, :]) @ Vh
+    b2 = wr - wl @ R
+    T = torch.eye(4, device=G.device, dtype=G.dtype).repeat(G.shape[0], 1, 1)
+    T[:, :3, :3] = R.transpose(1, 2)
+    T[:, :3, 3] = b2[:, 0]
+    return T
+
+
+def _ume_like(rng, shape_prefix, C, spread=20.0):
+    """UME-like matrices: [sum f | sum f x] of random neighbourhoods (well conditioned, absolute coordinates)."""
+    n_nb = 40
+    f = rng.uniform(0.1, 1.0, size=shape_prefix + (n_nb, C))
+    x = rng.normal(size=shape_prefix + (n_nb, 3)) * 3.0 + rng.uniform(-spread, spread, size=shape_prefix + (1, 3))
+    F0 = f.sum(-2)[..., None]
+    F1 = np.einsum("...kc,...kd->...cd", f, x)
+    F = np.concatenate([F0, F1], -1)
+    return (F / F0.sum(-2, keepdims=True)).astype(np.float32)
+
+
+@pytest.mark.parametrize("B,n1,n2,C", [(2, 40, 33, 32), (1, 70, 70, 64), (1, 19, 50, 16), (1, 24, 24, 100)])
+def test_ume_cdist_backward_kernels_against_torch_autograd(ume, B, n1, n2, C):
+    from umeregrobust_b200 import training
+    rng = np.random.default_rng(B * 1000 + n1 + C)
+    u1, u2 = _ume_like(rng, (B, n1), C), _ume_like(rng, (B, n2), C)
+    u2[:, : min(n1, n2) // 2] = u1[:, : min(n1, n2) // 2] * 1.01 + rng.normal(scale=1e-3, size=u1[:, : min(n1, n2) // 2].shape).astype(np.float32)
+    w = rng.normal(size=(B, n1, n2)).astype(np.float32)
+    a1, a2 = dev(u1).requires_grad_(True), dev(u2).requires_grad_(True)
+    D = training.ume_cdist_autograd(a1, a2)
+    (D * dev(w)).sum().backward()
+    # reference: torch autograd in float64 through QR / projectors / cdist
+    r1, r2 = dev(u1).double().requires_grad_(True), dev(u2).double().requires_grad_(True)
+    Dr = _torch_ume_cdist(r1, r2)
+    (Dr * dev(w).double()).sum().backward()
+    assert np.abs(host(D) - host(Dr)).max() < 2e-3                       # (sqrt of fp32 rounding near D = 0, see DESIGN §3.2)
+    for got, ref in ((a1.grad, r1.grad), (a2.grad, r2.grad)):
+        got, ref = host(got), host(ref)
+        # gradients blow up like 1 / D near D = 0 (the near-duplicates planted above): compare per matrix, relative
+        # to the matrix's own gradient norm
+        num = np.sqrt(((got - ref) ** 2).sum((-1, -2)))
+        den = np.sqrt((ref ** 2).sum((-1, -2))) + 1e-12
+        assert np.median(num / den) < 1e-4, float(np.median(num / den))
+        assert (num / den).max() < 2e-2, float((num / den).max())
+
+
+@pytest.mark.parametrize("nb,C", [(300, 32), (64, 64), (50, 20)])
+def test_rigid_solve_backward_kernel_against_torch_autograd(ume, nb, C):
+    from umeregrobust_b200 import training
+    rng = np.random.default_rng(nb + C)
+    G = _ume_like(rng, (nb,), C)
+    # H = G seen after a rigid motion, plus noise (so that the solve is meaningful), a few reflections-in-disguise
+    H = G.copy()
+    for i in range(nb):
+        T = synth.random_rigid(rng, t_range=(0.0, 10.0), max_tilt_deg=30.0)
+        H[i, :, 1:] = G[i, :, 1:] @ T[:3, :3].T + G[i, :, :1] * T[:3, 3]
+    H += rng.normal(scale=2e-3, size=H.shape).astype(np.float32) * np.abs(H).mean()
+    w = rng.normal(size=(nb, 4, 4)).astype(np.float32)
+    g, h = dev(G).requires_grad_(True), dev(H).requires_grad_(True)
+    T = training.rigid_from_ume_autograd(g, h)
+    (T * dev(w)).sum().backward()
+    gr, hr = dev(G).double().requires_grad_(True), dev(H).double().requires_grad_(True)
+    Tr = _torch_rigid_from_ume(gr, hr)
+    (Tr * dev(w).double()).sum().backward()
+    assert np.abs(host(T) - host(Tr)).max() < 5e-4
+    for got, ref in ((g.grad, gr.grad), (h.grad, hr.grad)):
+        got, ref = host(got), host(ref)
+        num = np.sqrt(((got - ref) ** 2).sum((-1, -2)))
+        den = np.sqrt((ref ** 2).sum((-1, -2))) + 1e-12
+        assert np.median(num / den) < 2e-3, float(np.median(num / den))
+        assert np.percentile(num / den, 95) < 2e-2, float(np.percentile(num / den, 95))

@@ -18,30 +18,9 @@ rng = np.random.default_rng(0)
 ss, ts = rng.choice(40000, Ns, replace=False), rng.choice(40000, Ns, replace=False)
 args = (d["src_pts"][:, ss].contiguous(), d["tgt_pts"][:, ts].contiguous(), d["src_feat"][:, ss].contiguous(), d["tgt_feat"][:, ts].contiguous(), T)
 corr = ume.FeatureCorrelator(sigma=1.5, batch=64, n_hypotheses=10)
-# the round-1 thread-per-query kernel as the reference for the tile kernel: same scores up to summation order
-ume.config["corr_thread"] = True
-for _ in range(2):
-    sc_thr, best_thr = corr.scores(*args)
-torch.cuda.synchronize()
-t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-t0.record(); sc_thr, best_thr = corr.scores(*args); t1.record(); torch.cuda.synchronize()
-ms_thr = t0.elapsed_time(t1)
-ume.config["corr_thread"] = False
 for _ in range(2):
     sc, best = corr.scores(*args)
 torch.cuda.synchronize()
-rel = float(((sc - sc_thr).abs() / sc_thr.abs().clamp_min(1e-6)).max())
-print("tile kernel vs thread-per-query kernel: max relative score difference %.2e, same best: %s (thread kernel: %.2f ms per pair)"
-      % (rel, int(best) == int(best_thr), ms_thr))
-import ctypes
-st = (ctypes.c_uint64 * 8)()
-_lib.lib().ume_corr_stats(1, None)
-corr.scores(*args)
-torch.cuda.synchronize()
-_lib.lib().ume_corr_stats(0, st)
-st = list(st)
-print("tile path: %.1f%% of the queries (fallback %.1f%%), %.0f staged candidates per (tile, hypothesis), %.1f%% of the items did not fit, %.1f%% had fewer than K candidates"
-      % (100.0 * st[0] / max(st[0] + st[1], 1), 100.0 * st[1] / max(st[0] + st[1], 1), st[2] / max(st[3], 1), 100.0 * st[4] / max(st[3], 1), 100.0 * st[5] / max(st[3], 1)))
 _lib.profile_reset(); _lib.profile_enable(True)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()

@@ -22,7 +22,6 @@ UME_FLAG_CELL_DIV2 = 2
 UME_FLAG_CTA_MOMENTS = 4
 UME_FLAG_RAW_MOMENTS = 8
 UME_FLAG_WARP_MOMENTS = 16
-UME_FLAG_CORR_THREAD = 32
 
 _lock = threading.Lock()
 _lib = None
@@ -98,6 +97,9 @@ def _bind(lib):
         "ume_pair_dist_f32": (i32, [vp, vp, i64, i32, f32, vp, vp]),
         "ume_rigid_solve_f32": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
         "ume_rotation_error_deg_f32": (i32, [vp, vp, i64, i32, i32, vp, vp]),
+        "ume_rigid_solve_backward_f32": (i32, [vp, vp, vp, i64, i32, vp, vp, vp]),
+        "ume_cdist_backward_workspace_bytes": (sz, [i32, i32, i32, i32]),
+        "ume_cdist_backward_f32": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]),
         "ume_gumbel_topk_f32": (i32, [vp, vp, i32, i32, i32, f32, c.c_uint64, vp, vp]),
         "ume_knn1_workspace_bytes": (sz, [i32, i32, i32]),
         "ume_knn1_gather_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, u32, vp, vp, vp, vp, sz, vp]),
@@ -109,7 +111,6 @@ def _bind(lib):
         "ume_linear_sum_assignment_host_f32": (i32, [vp, i32, i32, vp, vp]),
         "ume_voxel_unique_workspace_bytes": (sz, [i32]),
         "ume_voxel_unique_f32": (i32, [vp, i32, f32, vp, vp, vp, vp, sz, vp]),
-        "ume_corr_stats": (i32, [i32, vp]),
         "ume_corr_scores_workspace_bytes": (sz, [i32, i32, i32]),
         "ume_corr_scores_f32": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, u32, vp, vp, vp, sz, vp]),
     }
@@ -130,7 +131,8 @@ EXPORTED_SYMBOLS = ["ume_abi_version", "ume_last_error", "ume_status_string", "u
                     "ume_corr_scores_workspace_bytes", "ume_corr_scores_f32",
                     "ume_voxel_unique_workspace_bytes", "ume_voxel_unique_f32",
                     "ume_moments_backward_f32", "ume_neighbor_count_f32", "ume_linear_sum_assignment_host_f32",
-                    "ume_rotation_error_deg_f32", "ume_gumbel_topk_f32", "ume_orthonormalize_split_f32", "ume_cdist_split_f16", "ume_corr_stats"]
+                    "ume_rotation_error_deg_f32", "ume_gumbel_topk_f32", "ume_orthonormalize_split_f32", "ume_cdist_split_f16",
+                    "ume_rigid_solve_backward_f32", "ume_cdist_backward_workspace_bytes", "ume_cdist_backward_f32"]
 
 
 def lib():

@@ -24,9 +24,7 @@ _KNN = collections.namedtuple("_KNN", ["dists", "idx", "knn"])
 #              (default: warp kernel for C in {16,32,64,128} and launches of >= 3072 keypoints)
 #   cdist_impl: 0 = fp32 SIMT distance kernel, 1 = tcgen05 tensor-core kernel
 #               (C = 32 / 64 only), None = tensor cores whenever the channel count allows
-#   corr_thread: hypothesis scoring with the round-1 thread-per-query kernel instead of the tile kernel
-config = {"fma_dist": False, "cell_div2": False, "cdist_impl": None, "cta_moments": False, "warp_moments": False,
-          "corr_thread": False}
+config = {"fma_dist": False, "cell_div2": False, "cdist_impl": None, "cta_moments": False, "warp_moments": False}
 
 _workspaces = {}
 _workspaces_lock = threading.Lock()
@@ -35,8 +33,7 @@ _workspaces_lock = threading.Lock()
 def _flags():
     return ((_lib.UME_FLAG_FMA_DIST if config["fma_dist"] else 0) | (_lib.UME_FLAG_CELL_DIV2 if config["cell_div2"] else 0)
             | (_lib.UME_FLAG_CTA_MOMENTS if config["cta_moments"] is True else 0)
-            | (_lib.UME_FLAG_WARP_MOMENTS if config["cta_moments"] is False and config.get("warp_moments") else 0)
-            | (_lib.UME_FLAG_CORR_THREAD if config.get("corr_thread") else 0))
+            | (_lib.UME_FLAG_WARP_MOMENTS if config["cta_moments"] is False and config.get("warp_moments") else 0))
 
 
 def _stream():
@@ -406,6 +403,45 @@ def rigid_solve(G, H, gi=None, hi=None, offG=None, offH=None, buf=None):
                                             nm, C, _ptr(T), _stream())
     _lib.check(rc, "rigid_solve")
     return T
+
+
+def rigid_solve_backward(G, H, gT):
+    """Gradient of `rigid_solve(G[None], H[None])[0]` (pairing G[i] <-> H[i]) wrt G and H: G, H (nb,C,4),
+    gT (nb,4,4) -> (gG, gH).  The backward of utils/loc_utils.py:292-335 for loss.py:137-190."""
+    G = _dev_f32(G, "G", 3)
+    H = _dev_f32(H, "H", 3)
+    gT = _dev_f32(gT, "gT", 3)
+    nb, C, _ = G.shape
+    if H.shape != G.shape or G.shape[2] != 4 or tuple(gT.shape) != (nb, 4, 4):
+        raise ValueError("rigid_solve_backward: shapes %s, %s, %s do not agree" % (tuple(G.shape), tuple(H.shape), tuple(gT.shape)))
+    gG, gH = torch.empty_like(G), torch.empty_like(H)
+    with torch.cuda.device(G.device):
+        rc = _lib.lib().ume_rigid_solve_backward_f32(_ptr(G), _ptr(H), _ptr(gT), nb, C, _ptr(gG), _ptr(gH), _stream())
+    _lib.check(rc, "rigid_solve_backward")
+    return gG, gH
+
+
+def ume_cdist_backward(ume1, ume2, Qt1, Qt2, D, gD):
+    """Gradient of `ume_cdist(ume1, ume2)` wrt both arguments: ume1 (B,n1,C,4), ume2 (B,n2,C,4), their bases
+    Qt1 / Qt2 from `ume_descriptors`, the forward's D and its gradient gD (B,n1,n2) -> (g_ume1, g_ume2).
+    The backward of utils/loc_utils.py:8-15 for loss.py:84-118."""
+    ume1 = _dev_f32(ume1, "ume1", 4)
+    ume2 = _dev_f32(ume2, "ume2", 4)
+    Qt1, Qt2 = _dev_f32(Qt1, "Qt1", 4), _dev_f32(Qt2, "Qt2", 4)
+    D, gD = _dev_f32(D, "D", 3), _dev_f32(gD, "gD", 3)
+    B, n1, C, _ = ume1.shape
+    n2 = ume2.shape[1]
+    if (ume2.shape[0] != B or ume2.shape[2] != C or tuple(Qt1.shape) != (B, n1, 4, C) or tuple(Qt2.shape) != (B, n2, 4, C)
+            or tuple(D.shape) != (B, n1, n2) or tuple(gD.shape) != (B, n1, n2)):
+        raise ValueError("ume_cdist_backward: shapes do not agree")
+    g1, g2 = torch.empty_like(ume1), torch.empty_like(ume2)
+    L = _lib.lib()
+    with torch.cuda.device(ume1.device):
+        ws = _workspace(L.ume_cdist_backward_workspace_bytes(B, n1, n2, C), ume1.device)
+        rc = L.ume_cdist_backward_f32(_ptr(ume1), _ptr(ume2), _ptr(Qt1), _ptr(Qt2), _ptr(D), _ptr(gD), B, n1, n2, C,
+                                      _ptr(g1), _ptr(g2), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "ume_cdist_backward")
+    return g1, g2
 
 
 def batch_estimate_transform_ume_old(G, H):

@@ -9,12 +9,12 @@
 //
 // Correlation score (pc_corr, utils/loc_utils.py:592-619):
 //   score[h] = (1/Ns) sum_i sum_{k<K} cauchy(|T_h p_i - q_nn(i,k)|; sigma) <wf_src_i, wf_tgt_nn(i,k)>
-// One thread per (source point, hypothesis): the source points are taken in CELL ORDER of their own
-// grid, so the 128 threads of a CTA are spatial neighbours; under the same rigid transform they land
-// in the same few target cells and share candidates and target feature rows through L1.  The source
-// feature (C floats) stays in registers across the thread's loop over hypotheses.
+// One thread per (source point, hypothesis) for the search: the source points are taken in CELL ORDER of
+// their own grid, so the 128 threads of a CTA are spatial neighbours; under the same rigid transform they
+// land in the same few target cells and share candidates through L1.  The K x 32 feature dot products of a
+// warp's queries are then formed by the warp together, C/4 lanes per (query, neighbour): a target feature
+// row is read as one 128-byte line instead of 32 lanes gathering 16 bytes from 32 different rows.
 #include "ume_common.cuh"
-#include "corr_tile.cuh"
 
 #include <algorithm>
 
@@ -47,6 +47,7 @@ UME_DEVI void topk_insert(float (&bd)[KMAX], int (&bj)[KMAX], int& n, int K, flo
 // K best in a per-thread array (local memory), any K <= KMAX.
 template <int KMAX>
 struct ArrayTopK {
+    static constexpr int kCap = KMAX;
     float bd[KMAX];
     int bj[KMAX];
     int n, K;
@@ -65,6 +66,7 @@ struct ArrayTopK {
 // Insertion is one fully unrolled carry pass — no local memory, no data-dependent loop.
 template <int K_>
 struct RegTopK {
+    static constexpr int kCap = K_;
     float bd[K_];
     int bj[K_];
     UME_DEVI void reset(int) {
@@ -246,9 +248,11 @@ struct CorrParams {
 template <int C4, typename Top, bool kFma>
 __global__ void __launch_bounds__(kCorrThreads, UME_CORR_MINB) corr_score_kernel(CorrParams p) {
     __shared__ float s_red[kCorrThreads / 32];
-    // the thread's source feature row lives in shared memory ([chunk][thread]: conflict-free 16-byte
-    // reads), not in 4*C4 registers: the K-best list already takes 2K of them
-    __shared__ float4 s_sf[C4][kCorrThreads];
+    // the K neighbours of every thread's query, [k][thread]: weight and target row.  The dot products are
+    // then formed by the warp together — C4 lanes per (query, neighbour) read one feature row as one 128-byte
+    // line (one L1 wavefront) instead of 32 lanes gathering 16 bytes from 32 different lines
+    __shared__ float s_w[Top::kCap][kCorrThreads];
+    __shared__ int s_r[Top::kCap][kCorrThreads];
     const GridHeader hs = p.src_grid.hdr[0];
     const GridHeader ht = p.tgt_grid.hdr[0];
     const int* cs = p.tgt_grid.cell_start;
@@ -256,36 +260,46 @@ __global__ void __launch_bounds__(kCorrThreads, UME_CORR_MINB) corr_score_kernel
     const int t = blockIdx.x * kCorrThreads + threadIdx.x;
     const bool active = t < hs.n_sorted;
     float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
-        me = p.src_grid.sorted[t];
-        const float* row = p.wf_src + (size_t)__float_as_int(me.w) * (C4 * 4);
-#pragma unroll
-        for (int c = 0; c < C4; ++c) s_sf[c][threadIdx.x] = ldg_f4(row + 4 * c);
-    }
+    if (active) me = p.src_grid.sorted[t];
+    const int my_row = __float_as_int(me.w);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int PP = 32 / C4;
+    const int gq = lane / C4, ch = lane % C4;
+    const int K = p.K;
     for (int hyp = blockIdx.y; hyp < p.n_hyp; hyp += gridDim.y) {
         const float* T = p.T + (size_t)hyp * 16;
-        float acc = 0.f;
+        int n_found = 0;
         if (active) {
             // source_points @ R^T + t  (utils/loc_utils.py:626), row-times-matrix in fp32
             const float qx = fmaf(me.z, __ldg(T + 2), fmaf(me.y, __ldg(T + 1), me.x * __ldg(T + 0))) + __ldg(T + 3);
             const float qy = fmaf(me.z, __ldg(T + 6), fmaf(me.y, __ldg(T + 5), me.x * __ldg(T + 4))) + __ldg(T + 7);
             const float qz = fmaf(me.z, __ldg(T + 10), fmaf(me.y, __ldg(T + 9), me.x * __ldg(T + 8))) + __ldg(T + 11);
             Top top;
-            top.reset(p.K);
+            top.reset(K);
             grid_knn<kFma>(ht, cs, tgt_sorted, qx, qy, qz, top);
             top.for_each([&](float dk, int jk) {
-                const float* row = p.wf_tgt + (size_t)jk * (C4 * 4);
-                float v = 0.f;
-#pragma unroll
-                for (int c = 0; c < C4; ++c) {
-                    const float4 g = ldg_f4(row + 4 * c);
-                    const float4 a = s_sf[c][threadIdx.x];
-                    v = fmaf(a.x, g.x, v); v = fmaf(a.y, g.y, v); v = fmaf(a.z, g.z, v); v = fmaf(a.w, g.w, v);
-                }
                 const float e = sqrtf(dk) * p.inv_sigma;             // |p - q| / sigma
-                acc = fmaf(v, 1.f / fmaf(e, e, 1.f), acc);            // cauchy_kernel (:588-589)
+                s_w[n_found][threadIdx.x] = 1.f / fmaf(e, e, 1.f);   // cauchy_kernel (:588-589)
+                s_r[n_found][threadIdx.x] = jk;
+                ++n_found;
             });
+        }
+        for (int k = n_found; k < K; ++k) { s_w[k][threadIdx.x] = 0.f; s_r[k][threadIdx.x] = 0; }   // (fewer than K rows in the cloud)
+        __syncwarp();
+        float acc = 0.f;
+        for (int q = 0; q < 32; ++q) {
+            const int row_q = __shfl_sync(UME_FULL_MASK, my_row, q);
+            const float4 a = ldg_f4(p.wf_src + (size_t)row_q * (C4 * 4) + 4 * ch);
+            const int col = warp * 32 + q;
+#pragma unroll 5
+            for (int k0 = 0; k0 < K; k0 += PP) {
+                const int k = min(k0 + gq, K - 1);
+                const float wgt = (k0 + gq < K) ? s_w[k][col] : 0.f;
+                const float4 g = ldg_f4(p.wf_tgt + (size_t)s_r[k][col] * (C4 * 4) + 4 * ch);
+                float v = a.x * g.x;
+                v = fmaf(a.y, g.y, v); v = fmaf(a.z, g.z, v); v = fmaf(a.w, g.w, v);
+                acc = fmaf(v, wgt, acc);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(UME_FULL_MASK, acc, o);
@@ -297,316 +311,6 @@ __global__ void __launch_bounds__(kCorrThreads, UME_CORR_MINB) corr_score_kernel
             p.partial[(size_t)hyp * gridDim.x + blockIdx.x] = s;
         }
         __syncthreads();
-    }
-}
-
-// ---------------------------------------------------------------- correlation score, tile version
-// (design notes at the top of corr_tile.cuh)
-struct TileParams {
-    GridView src_grid;       // B = 1: the source cloud in cell order
-    GridView tgt_grid;
-    const float* wf_src;     // (Ns, C)
-    const float* wf_tgt;     // (Nt, C)
-    const float* T;          // (n_hyp, 4, 4)
-    float* partial;          // (n_hyp, nslots)
-    int* tiles;              // [0] = number of tiles, then (start, len) pairs
-    unsigned long long* stats;   // optional: [0] lanes served by the tile path, [1] by the ring-search fallback
-    int n_hyp, K, nslots;
-    float inv_sigma;
-};
-
-// Tiles = runs of <= 32 consecutive entries of the source's cell-sorted array that do not cross a cell
-// row (a tile that wrapped from the end of one row to the start of the next would span the cloud).
-__global__ void __launch_bounds__(1024) corr_tiles_kernel(GridView g, int* __restrict__ tiles, int max_tiles) {
-    __shared__ int warp_tot[32];
-    __shared__ int running;
-    const GridHeader h = g.hdr[0];
-    const int nrows = h.ny * h.nz;
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    if (t == 0) running = 0;
-    __syncthreads();
-    for (int base = 0; base < nrows; base += 1024) {
-        const int r = base + t;
-        int s = 0, n = 0;
-        if (r < nrows) {
-            s = g.cell_start[r * h.nx];
-            n = g.cell_start[(r + 1) * h.nx] - s;
-        }
-        const int nt = (n + 31) >> 5;
-        int incl = nt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(UME_FULL_MASK, incl, o);
-            if (lane >= o) incl += u;
-        }
-        if (lane == 31) warp_tot[w] = incl;
-        __syncthreads();
-        int wbase = 0;
-        for (int k = 0; k < w; ++k) wbase += warp_tot[k];
-        const int run0 = running;
-        int at = run0 + wbase + incl - nt;
-        for (int k = 0; k < nt && at < max_tiles; ++k, ++at) {
-            tiles[1 + 2 * at] = s + 32 * k;
-            tiles[2 + 2 * at] = min(32, n - 32 * k);
-        }
-        __syncthreads();
-        if (t == 1023) running = run0 + wbase + incl;
-        __syncthreads();
-    }
-    if (t == 0) tiles[0] = min(running, max_tiles);
-}
-
-#ifndef UME_TILE_RHO
-#define UME_TILE_RHO 1.3f           // staged radius = this x the K-NN radius estimated from the tile's own density
-#endif
-
-// One query (ax, ay, az) against the M staged candidates, lane = candidate (S slots per lane): finds the K
-// nearest among those closer than sqrt(m2) and adds lane k's k-th neighbour contribution to `acc`.  Returns
-// false (warp-uniform) when the K nearest are not all inside the margin.  `qi` = the query's row of sm.sf.
-template <int S, int C4, bool kFma>
-UME_DEVI bool tile_one_query(tile::WarpSmem<C4>& sm, int M, int K, float ax, float ay, float az, float m2, float tau0, int qi,
-                             const float* __restrict__ wf_tgt, float inv_sigma, float& acc) {
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = lanemask_lt();
-    float d[S];
-#pragma unroll
-    for (int j = 0; j < S; ++j) {
-        const int c = j * 32 + lane;
-        const float4 cd = sm.cand[c < M ? c : 0];
-        const float v = dist2_ordered<kFma>(__fsub_rn(ax, cd.x), __fsub_rn(ay, cd.y), __fsub_rn(az, cd.z));
-        d[j] = c < M ? v : INFINITY;
-    }
-    auto count_lt = [&](float tau) {
-        int n = 0;
-#pragma unroll
-        for (int j = 0; j < S; ++j) n += (d[j] < tau) ? 1 : 0;
-        return __reduce_add_sync(UME_FULL_MASK, n);
-    };
-    // a threshold with exactly K candidates below it, inside [0, margin^2]
-    float lo = 0.f, hi = m2, tau = m2;
-    int n_hi = count_lt(m2);
-    if (n_hi < K) return false;                                // the K nearest are not all inside the margin
-    int n_tau = n_hi, n_lo = 0;
-    if (n_hi > K) {
-        float probe = fminf(tau0, 0.5f * m2);
-        bool done = false;
-        for (int it = 0; it < 64 && !done; ++it) {
-            const int n = count_lt(probe);
-            if (n == K) { tau = probe; n_tau = n; done = true; break; }
-            if (n < K) { lo = probe; n_lo = n; } else { hi = probe; n_hi = n; }
-            const float mid = 0.5f * (lo + hi);
-            if (!(mid > lo && mid < hi)) { tau = hi; n_tau = n_hi; done = true; break; }   // no float strictly inside: ties straddle K
-            probe = mid;
-        }
-        if (!done) return false;                               // (K or more candidates at distance ~0: leave it to the ring search)
-    }
-    // selected: everything below tau; when ties straddle K (n_tau > K) the candidates in [lo, tau) are all
-    // EQUAL in distance and the (K - n_lo) lowest rows among them win
-    unsigned pick = 0;                                         // bit j: this lane's slot j is a neighbour
-    if (n_tau == K) {
-#pragma unroll
-        for (int j = 0; j < S; ++j) pick |= (d[j] < tau) ? (1u << j) : 0u;
-    } else {
-        int rows[S];
-        unsigned tied = 0;
-#pragma unroll
-        for (int j = 0; j < S; ++j) {
-            const int c = j * 32 + lane;
-            rows[j] = __float_as_int(sm.cand[c < M ? c : 0].w);
-            pick |= (d[j] < lo) ? (1u << j) : 0u;
-            tied |= (d[j] >= lo && d[j] < tau) ? (1u << j) : 0u;
-        }
-        for (int need = K - n_lo; need > 0; --need) {          // rare: one warp-wide arg-min per tied winner
-            int best = 0x7fffffff;
-#pragma unroll
-            for (int j = 0; j < S; ++j) best = ((tied >> j) & 1u) ? min(best, rows[j]) : best;
-            best = __reduce_min_sync(UME_FULL_MASK, best);
-#pragma unroll
-            for (int j = 0; j < S; ++j)
-                if (((tied >> j) & 1u) && rows[j] == best) { tied &= ~(1u << j); pick |= 1u << j; }
-        }
-    }
-    // squeeze the K neighbours into the list
-    int base = 0;
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < S; ++j) {
-        const bool take = (pick >> j) & 1u;
-        const unsigned m = __ballot_sync(UME_FULL_MASK, take);
-        if (take) {
-            const int at = base + __popc(m & lt);
-            sm.sel_d2[at] = d[j];
-            sm.sel_row[at] = __float_as_int(sm.cand[j * 32 + lane].w);
-        }
-        base += __popc(m);
-    }
-    __syncwarp();
-    // K dot products in parallel: lane k takes the k-th neighbour
-    if (lane < K) {
-        const float dk = sm.sel_d2[lane];
-        const float* row = wf_tgt + (size_t)sm.sel_row[lane] * (C4 * 4);
-        float v = 0.f;
-#pragma unroll
-        for (int c = 0; c < C4; ++c) {
-            const float4 g = ldg_f4(row + 4 * c);
-            const float4 a = sm.sf[qi][c];                     // broadcast
-            v = fmaf(a.x, g.x, v); v = fmaf(a.y, g.y, v); v = fmaf(a.z, g.z, v); v = fmaf(a.w, g.w, v);
-        }
-        const float e = sqrtf(dk) * inv_sigma;                 // |p - q| / sigma
-        acc = fmaf(v, 1.f / fmaf(e, e, 1.f), acc);              // cauchy_kernel (:588-589)
-    }
-    return true;
-}
-
-template <int C4, bool kFma>
-UME_DEVI bool tile_one_query_any(tile::WarpSmem<C4>& sm, int M, int K, float ax, float ay, float az, float m2, float tau0,
-                                 int qi, const float* __restrict__ wf_tgt, float inv_sigma, float& acc) {
-    if (M <= 32 * 4) return tile_one_query<4, C4, kFma>(sm, M, K, ax, ay, az, m2, tau0, qi, wf_tgt, inv_sigma, acc);
-    if (M <= 32 * 7) return tile_one_query<7, C4, kFma>(sm, M, K, ax, ay, az, m2, tau0, qi, wf_tgt, inv_sigma, acc);
-    return tile_one_query<tile::kSlotsMax, C4, kFma>(sm, M, K, ax, ay, az, m2, tau0, qi, wf_tgt, inv_sigma, acc);
-}
-
-// squared distance from q to the nearest face of the cell block [c0, c1] that has target points beyond it
-// (faces on the grid's boundary do not count: every target point lies inside the grid), shrunk by a safety
-// factor, and capped by the distance to the block's farthest corner (a finite range for the bisection)
-UME_DEVI float block_margin2(const GridHeader& ht, float qx, float qy, float qz, int cx0, int cx1, int cy0, int cy1, int cz0, int cz1) {
-    const float inf = INFINITY;
-    const float xl = ht.ox + (float)cx0 * ht.s, xh = ht.ox + (float)(cx1 + 1) * ht.s;
-    const float yl = ht.oy + (float)cy0 * ht.s, yh = ht.oy + (float)(cy1 + 1) * ht.s;
-    const float zl = ht.oz + (float)cz0 * ht.s, zh = ht.oz + (float)(cz1 + 1) * ht.s;
-    float mg = fminf(fminf(fminf(cx0 == 0 ? inf : qx - xl, cx1 == ht.nx - 1 ? inf : xh - qx),
-                           fminf(cy0 == 0 ? inf : qy - yl, cy1 == ht.ny - 1 ? inf : yh - qy)),
-                     fminf(cz0 == 0 ? inf : qz - zl, cz1 == ht.nz - 1 ? inf : zh - qz));
-    const float fx = fmaxf(fabsf(qx - xl), fabsf(qx - xh)), fy = fmaxf(fabsf(qy - yl), fabsf(qy - yh)),
-                fz = fmaxf(fabsf(qz - zl), fabsf(qz - zh));
-    const float far = sqrtf(fx * fx + fy * fy + fz * fz) * 1.001f + 1e-3f * ht.s;
-    mg = fminf(fmaxf(mg * 0.9999f - 1e-4f * ht.s, 0.f), far);
-    return mg * mg;
-}
-
-template <int C4, typename Top, bool kFma>
-__global__ void __launch_bounds__(32 * tile::kWarps, 4) corr_tile_kernel(TileParams p) {
-    extern __shared__ __align__(16) unsigned char tile_smem_raw[];
-    using WS = tile::WarpSmem<C4>;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WS& sm = reinterpret_cast<WS*>(tile_smem_raw)[warp];
-    const GridHeader ht = p.tgt_grid.hdr[0];
-    const int* cs = p.tgt_grid.cell_start;
-    const float4* tgt_sorted = p.tgt_grid.sorted;
-    const float4* src_sorted = p.src_grid.sorted;
-    const int n_tiles = p.tiles[0];
-    const int slot = blockIdx.x * tile::kWarps + warp;
-    const int K = p.K;
-    unsigned long long n_fast = 0, n_slow = 0;
-
-    for (int hyp = blockIdx.y; hyp < p.n_hyp; hyp += gridDim.y) {
-        const float* T = p.T + (size_t)hyp * 16;
-        const float t00 = __ldg(T + 0), t01 = __ldg(T + 1), t02 = __ldg(T + 2), t03 = __ldg(T + 3);
-        const float t10 = __ldg(T + 4), t11 = __ldg(T + 5), t12 = __ldg(T + 6), t13 = __ldg(T + 7);
-        const float t20 = __ldg(T + 8), t21 = __ldg(T + 9), t22 = __ldg(T + 10), t23 = __ldg(T + 11);
-        float score = 0.f;                                     // this slot's share of the hypothesis, fixed tile order
-        for (int tl = slot; tl < n_tiles; tl += p.nslots) {
-            const int t0 = p.tiles[1 + 2 * tl], tn = p.tiles[2 + 2 * tl];
-            const bool active = lane < tn;
-            float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncwarp();                                      // the previous tile's readers are done with sm
-            if (active) {
-                me = __ldg(&src_sorted[t0 + lane]);
-                const float* row = p.wf_src + (size_t)__float_as_int(me.w) * (C4 * 4);
-#pragma unroll
-                for (int c = 0; c < C4; ++c) sm.sf[lane][c] = ldg_f4(row + 4 * c);
-            }
-            // source_points @ R^T + t  (utils/loc_utils.py:626), row-times-matrix in fp32
-            const float qx = fmaf(me.z, t02, fmaf(me.y, t01, me.x * t00)) + t03;
-            const float qy = fmaf(me.z, t12, fmaf(me.y, t11, me.x * t10)) + t13;
-            const float qz = fmaf(me.z, t22, fmaf(me.y, t21, me.x * t20)) + t23;
-            // the tile's landing zone and the radius that should hold K target points around any of its queries
-            const float bx0 = tile::warp_min(active ? qx : INFINITY), bx1 = tile::warp_max(active ? qx : -INFINITY);
-            const float by0 = tile::warp_min(active ? qy : INFINITY), by1 = tile::warp_max(active ? qy : -INFINITY);
-            const float bz0 = tile::warp_min(active ? qz : INFINITY), bz1 = tile::warp_max(active ? qz : -INFINITY);
-            const float dx = bx1 - bx0, dy = by1 - by0, dz = bz1 - bz0;
-            const float area = fmaxf(dx * dy, fmaxf(dx * dz, dy * dz));
-            const float rk = sqrtf((float)K * area / (3.14159265f * (float)tn));     // K-NN radius at the tile's own density
-            float rho = fminf(fmaxf(UME_TILE_RHO * rk, 0.5f * ht.s), 6.f * ht.s);
-            const bool finite = isfinite(dx) && isfinite(dy) && isfinite(dz);
-            int M = -1;
-            int cx0 = 0, cx1 = 0, cy0 = 0, cy1 = 0, cz0 = 0, cz1 = 0;
-            if (finite) {
-                // too many candidates: half the radius; too few: twice the radius (at most three stagings)
-                bool shrunk = false, grown = false;
-                for (int attempt = 0; attempt < 3; ++attempt) {
-                    cx0 = cell_coord(bx0 - rho, ht.ox, ht.inv_s, ht.nx); cx1 = cell_coord(bx1 + rho, ht.ox, ht.inv_s, ht.nx);
-                    cy0 = cell_coord(by0 - rho, ht.oy, ht.inv_s, ht.ny); cy1 = cell_coord(by1 + rho, ht.oy, ht.inv_s, ht.ny);
-                    cz0 = cell_coord(bz0 - rho, ht.oz, ht.inv_s, ht.nz); cz1 = cell_coord(bz1 + rho, ht.oz, ht.inv_s, ht.nz);
-                    M = tile::stage_block<C4>(sm, ht, cs, tgt_sorted, cx0, cx1, cy0, cy1, cz0, cz1);
-                    if (M < 0 && !grown) { rho *= 0.5f; shrunk = true; }
-                    else if (M >= 0 && M < 2 * K && !shrunk) { rho *= 2.f; grown = true; }
-                    else break;
-                }
-            }
-            unsigned failed = 0xffffffffu >> (32 - tn);        // queries still to be served by the ring search
-            float acc = 0.f;
-            if (M >= K) {                                      // warp-uniform
-                const float margin2 = block_margin2(ht, qx, qy, qz, cx0, cx1, cy0, cy1, cz0, cz1);
-                const float tau0 = rk * rk;
-                unsigned again = 0u;                           // queries whose K nearest reach past their margin
-                for (int i = 0; i < tn; ++i) {
-                    const float ax = __shfl_sync(UME_FULL_MASK, qx, i), ay = __shfl_sync(UME_FULL_MASK, qy, i),
-                                az = __shfl_sync(UME_FULL_MASK, qz, i), m2 = __shfl_sync(UME_FULL_MASK, margin2, i);
-                    if (!tile_one_query_any<C4, kFma>(sm, M, K, ax, ay, az, m2, tau0, i, p.wf_tgt, p.inv_sigma, acc)) again |= 1u << i;
-                }
-                // second chance, query by query: a block of its own around the query, twice the radius
-                failed = 0u;
-                const float rho2 = fminf(2.2f * fmaxf(rho, rk), 8.f * ht.s);
-                while (again) {
-                    const int i = __ffs(again) - 1;
-                    again &= again - 1;
-                    const float ax = __shfl_sync(UME_FULL_MASK, qx, i), ay = __shfl_sync(UME_FULL_MASK, qy, i),
-                                az = __shfl_sync(UME_FULL_MASK, qz, i);
-                    const int ax0 = cell_coord(ax - rho2, ht.ox, ht.inv_s, ht.nx), ax1 = cell_coord(ax + rho2, ht.ox, ht.inv_s, ht.nx);
-                    const int ay0 = cell_coord(ay - rho2, ht.oy, ht.inv_s, ht.ny), ay1 = cell_coord(ay + rho2, ht.oy, ht.inv_s, ht.ny);
-                    const int az0 = cell_coord(az - rho2, ht.oz, ht.inv_s, ht.nz), az1 = cell_coord(az + rho2, ht.oz, ht.inv_s, ht.nz);
-                    const int M2 = tile::stage_block<C4>(sm, ht, cs, tgt_sorted, ax0, ax1, ay0, ay1, az0, az1);
-                    bool ok = false;
-                    if (M2 >= K) {
-                        const float m2 = block_margin2(ht, ax, ay, az, ax0, ax1, ay0, ay1, az0, az1);
-                        ok = tile_one_query_any<C4, kFma>(sm, M2, K, ax, ay, az, m2, 4.f * tau0, i, p.wf_tgt, p.inv_sigma, acc);
-                    }
-                    if (!ok) failed |= 1u << i;
-                }
-            }
-            if (active && ((failed >> lane) & 1u)) {
-                // sparse or far-away landing zone, more candidates than fit: the exact ring search of round 1
-                Top top;
-                top.reset(K);
-                grid_knn<kFma>(ht, cs, tgt_sorted, qx, qy, qz, top);
-                top.for_each([&](float dk, int jk) {
-                    const float* row = p.wf_tgt + (size_t)jk * (C4 * 4);
-                    float v = 0.f;
-#pragma unroll
-                    for (int c = 0; c < C4; ++c) {
-                        const float4 g = ldg_f4(row + 4 * c);
-                        const float4 a = sm.sf[lane][c];
-                        v = fmaf(a.x, g.x, v); v = fmaf(a.y, g.y, v); v = fmaf(a.z, g.z, v); v = fmaf(a.w, g.w, v);
-                    }
-                    const float e = sqrtf(dk) * p.inv_sigma;
-                    acc = fmaf(v, 1.f / fmaf(e, e, 1.f), acc);
-                });
-            }
-            if (p.stats) {
-                n_fast += tn - __popc(failed);
-                n_slow += __popc(failed);
-                if (lane == 0) { atomicAdd(&p.stats[2], (unsigned long long)max(M, 0)); atomicAdd(&p.stats[3], 1ull); if (M < 0) atomicAdd(&p.stats[4], 1ull); if (M >= 0 && M < K) atomicAdd(&p.stats[5], 1ull); }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(UME_FULL_MASK, acc, o);
-            score += acc;
-        }
-        if (lane == 0) p.partial[(size_t)hyp * p.nslots + slot] = score;
-    }
-    if (p.stats && lane == 0) {
-        atomicAdd(&p.stats[0], n_fast);
-        atomicAdd(&p.stats[1], n_slow);
     }
 }
 
@@ -738,39 +442,11 @@ extern "C" int ume_weight_features_f32(const float* f, const float* mean, const 
     return check_launch("weight_features_kernel");
 }
 
-namespace ume {
-namespace {
-
-// diagnostics (tools/bench_corr.py): lanes served by the tile path / by the fallback, staged candidates, tiles,
-// tiles whose block did not fit, tiles with fewer than K candidates
-__device__ unsigned long long g_corr_stats[8];
-bool g_corr_stats_on = false;
-
-constexpr int kTileSlotsX = 37;       // CTAs along the tiles: kTileSlotsX * tile::kWarps warp slots share the tiles
-
-template <int C4, bool kFma>
-int launch_tile(const TileParams& p, int K, dim3 grid, cudaStream_t stream) {
-    const size_t smem = sizeof(tile::WarpSmem<C4>) * tile::kWarps;
-    auto k20 = corr_tile_kernel<C4, RegTopK<20>, kFma>;
-    auto kany = corr_tile_kernel<C4, ArrayTopK<32>, kFma>;
-    cudaError_t e = cudaFuncSetAttribute(K == 20 ? k20 : kany, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    UME_REQUIRE(e == cudaSuccess, UME_ERR_CUDA, "corr_tile_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    if (K == 20) k20<<<grid, 32 * tile::kWarps, smem, stream>>>(p);
-    else kany<<<grid, 32 * tile::kWarps, smem, stream>>>(p);
-    return UME_OK;
-}
-
-}  // namespace
-}  // namespace ume
-
 extern "C" size_t ume_corr_scores_workspace_bytes(int Ns, int Nt, int n_hyp) {
     if (Ns <= 0 || Nt <= 0 || n_hyp <= 0) return 0;
     const size_t nb = (size_t)(Ns + ume::kCorrThreads - 1) / ume::kCorrThreads;
-    const size_t nslots = (size_t)ume::kTileSlotsX * ume::tile::kWarps;
-    const size_t max_tiles = (size_t)Ns / 32 + ume::kCellsCap + 1;
     return ume::grid_workspace_bytes(1, Ns, ume::kCellsCap) + ume::grid_workspace_bytes(1, Nt, ume::kCellsCap) +
-           ume::align_up((size_t)n_hyp * std::max(nb, nslots) * sizeof(float), 256) +
-           ume::align_up((1 + 2 * max_tiles) * sizeof(int), 256) + 1024;
+           ume::align_up((size_t)n_hyp * nb * sizeof(float), 256) + 1024;
 }
 
 extern "C" int ume_corr_scores_f32(const float* src_pts, const float* tgt_pts, const float* wf_src, const float* wf_tgt,
@@ -789,34 +465,6 @@ extern "C" int ume_corr_scores_f32(const float* src_pts, const float* tgt_pts, c
     UME_REQUIRE(ws && ws_bytes >= ume_corr_scores_workspace_bytes(Ns, Nt, n_hyp), UME_ERR_WORKSPACE,
                 "ume_corr_scores_f32: workspace too small");
     Workspace w(ws, ws_bytes);
-    const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
-    if (!(flags & UME_FLAG_CORR_THREAD)) {
-        // tile version (corr_tile.cuh): a warp per tile of 32 neighbouring source points, candidates staged once
-        TileParams p;
-        int rc = grid_build(src_pts, src_pts, 1, Ns, Ns, 0.f, -8.f, kCellsCap, w, &p.src_grid, stream);
-        if (rc != UME_OK) return rc;
-        rc = grid_build(tgt_pts, tgt_pts, 1, Nt, Nt, 0.f, -4.f, kCellsCap, w, &p.tgt_grid, stream);
-        if (rc != UME_OK) return rc;
-        const int max_tiles = Ns / 32 + kCellsCap + 1;
-        p.nslots = kTileSlotsX * tile::kWarps;
-        p.partial = w.take<float>((size_t)n_hyp * p.nslots);
-        p.tiles = w.take<int>((size_t)1 + 2 * max_tiles);
-        UME_REQUIRE(w.ok(), UME_ERR_WORKSPACE, "ume_corr_scores_f32: workspace too small");
-        p.stats = nullptr;
-        if (g_corr_stats_on) cudaGetSymbolAddress(reinterpret_cast<void**>(&p.stats), g_corr_stats);
-        p.wf_src = wf_src; p.wf_tgt = wf_tgt; p.T = T; p.n_hyp = n_hyp; p.K = K; p.inv_sigma = 1.f / sigma;
-        ProfScope prof(UME_PROF_CORR, stream);
-        corr_tiles_kernel<<<1, 1024, 0, stream>>>(p.src_grid, p.tiles, max_tiles);
-        // hypothesis groups: a few CTAs per SM in flight, several waves for balance
-        const int gy = max(1, min(n_hyp, 64));
-        dim3 grid((unsigned)kTileSlotsX, (unsigned)gy);
-        if (C == 32) rc = fma ? launch_tile<8, true>(p, K, grid, stream) : launch_tile<8, false>(p, K, grid, stream);
-        else rc = fma ? launch_tile<16, true>(p, K, grid, stream) : launch_tile<16, false>(p, K, grid, stream);
-        if (rc != UME_OK) return rc;
-        corr_finalize_kernel<<<1, 256, 0, stream>>>(p.partial, n_hyp, p.nslots, 1.f / (float)Ns, score, best);
-        count_launch(3);
-        return check_launch("corr_tile_kernel");
-    }
     CorrParams p;
     int rc = grid_build(src_pts, src_pts, 1, Ns, Ns, 0.f, -8.f, kCellsCap, w, &p.src_grid, stream);
     if (rc != UME_OK) return rc;
@@ -830,23 +478,10 @@ extern "C" int ume_corr_scores_f32(const float* src_pts, const float* tgt_pts, c
     int gy = (148 * 8 * 4 + nb - 1) / nb;
     gy = max(1, min(gy, min(n_hyp, 65535)));
     dim3 grid((unsigned)nb, (unsigned)gy);
+    const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
     ProfScope prof(UME_PROF_CORR, stream);
     launch_corr(p, C, K, fma, grid, stream);
     corr_finalize_kernel<<<1, 256, 0, stream>>>(p.partial, n_hyp, nb, 1.f / (float)Ns, score, best);
     count_launch(2);
     return check_launch("corr_score_kernel");
-}
-
-// Diagnostics of the tile kernel (not part of the measured path): enable / read-and-reset the counters.
-extern "C" int ume_corr_stats(int enable, uint64_t* out8_host) {
-    using namespace ume;
-    g_corr_stats_on = enable != 0;
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (out8_host) {
-        cudaError_t e = cudaMemcpyFromSymbol(out8_host, g_corr_stats, sizeof(z));
-        UME_REQUIRE(e == cudaSuccess, UME_ERR_CUDA, "ume_corr_stats: %s", cudaGetErrorString(e));
-    }
-    cudaError_t e = cudaMemcpyToSymbol(g_corr_stats, z, sizeof(z));
-    UME_REQUIRE(e == cudaSuccess, UME_ERR_CUDA, "ume_corr_stats: %s", cudaGetErrorString(e));
-    return UME_OK;
 }

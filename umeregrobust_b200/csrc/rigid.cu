@@ -48,8 +48,9 @@ UME_DEVI V3 normalized_or(const V3& a, const V3& fallback) {
     return fallback;
 }
 
-// A (row-major 3x3) -> R = U diag(1,1,det(U Vh)) Vh, row-major.
-UME_DEVI void rotation_from_cross_moment(const float A[9], float R[9]) {
+// A (row-major 3x3) -> the proper frames L = [l1 l2 l1xl2], Rr = [r1 r2 r1xr2] with A = L diag(s1, s2, +-s3) Rr^T
+// (the third "singular value" carries the sign of det(U Vh)): the reference's R = U diag(1,1,det(U Vh)) Vh is L Rr^T.
+UME_DEVI void svd_frames(const float A[9], V3 l[3], V3 r[3]) {
     // pre-scale: Jacobi is scale invariant, but squares of tiny / huge entries are not
     float amax = 0.f;
 #pragma unroll
@@ -83,9 +84,14 @@ UME_DEVI void rotation_from_cross_moment(const float A[9], float R[9]) {
         if (dot(cand, cand) < 1e-6f) cand = axpy(-dot(l1, r3), l1, r3);
         l2 = normalized_or(cand, V3{0.f, 1.f, 0.f});
     }
-    const V3 l3 = cross(l1, l2);
-    const float lx[3] = {l1.x, l2.x, l3.x}, ly[3] = {l1.y, l2.y, l3.y}, lz[3] = {l1.z, l2.z, l3.z};
-    const float rx[3] = {r1.x, r2.x, r3.x}, ry[3] = {r1.y, r2.y, r3.y}, rz[3] = {r1.z, r2.z, r3.z};
+    l[0] = l1; l[1] = l2; l[2] = cross(l1, l2);
+    r[0] = r1; r[1] = r2; r[2] = r3;
+}
+
+// R = L Rr^T, row-major
+UME_DEVI void rotation_from_frames(const V3 l[3], const V3 r[3], float R[9]) {
+    const float lx[3] = {l[0].x, l[1].x, l[2].x}, ly[3] = {l[0].y, l[1].y, l[2].y}, lz[3] = {l[0].z, l[1].z, l[2].z};
+    const float rx[3] = {r[0].x, r[1].x, r[2].x}, ry[3] = {r[0].y, r[1].y, r[2].y}, rz[3] = {r[0].z, r[1].z, r[2].z};
 #pragma unroll
     for (int k = 0; k < 9; ++k) R[k] = 0.f;
 #pragma unroll
@@ -94,6 +100,13 @@ UME_DEVI void rotation_from_cross_moment(const float A[9], float R[9]) {
         R[3] = fmaf(ly[k], rx[k], R[3]); R[4] = fmaf(ly[k], ry[k], R[4]); R[5] = fmaf(ly[k], rz[k], R[5]);
         R[6] = fmaf(lz[k], rx[k], R[6]); R[7] = fmaf(lz[k], ry[k], R[7]); R[8] = fmaf(lz[k], rz[k], R[8]);
     }
+}
+
+// A (row-major 3x3) -> R = U diag(1,1,det(U Vh)) Vh, row-major.
+UME_DEVI void rotation_from_cross_moment(const float A[9], float R[9]) {
+    V3 l[3], r[3];
+    svd_frames(A, l, r);
+    rotation_from_frames(l, r, R);
 }
 
 __global__ void __launch_bounds__(256) rigid_kernel(const float* __restrict__ G, const float* __restrict__ H,
@@ -167,6 +180,161 @@ __global__ void __launch_bounds__(256) rigid_kernel(const float* __restrict__ G,
     }
 }
 
+// Backward of the solve above for the training losses (loss.py:137-190 differentiates through
+// batch_estimate_transform_ume_old): gT (nb,4,4) -> gG, gH (nb,C,4).  Same decomposition as the forward:
+// eight lanes per hypothesis, the rows re-read from L1.  With A = L diag(s) Rr^T in proper frames (s3 signed) and
+// R = L Rr^T:  dR = L Z Rr^T,  Z antisymmetric,  Z_ij = (dP_ij - dP_ji) / (s_i + s_j),  dP = L^T dA Rr  — no
+// 1 / (s_i^2 - s_j^2) as in a generic SVD backward, so equal singular values are harmless.
+__global__ void __launch_bounds__(256) rigid_backward_kernel(const float* __restrict__ G, const float* __restrict__ H,
+                                                             const float* __restrict__ gT, int64_t total, int C,
+                                                             float* __restrict__ gG, float* __restrict__ gH) {
+    const int l8 = threadIdx.x & 7;
+    const int64_t hyp = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+    const bool valid = hyp < total;
+    const int64_t hc = valid ? hyp : 0;
+    const float* Gm = G + (size_t)hc * C * 4;
+    const float* Hm = H + (size_t)hc * C * 4;
+    // forward, pass 1
+    float s_mg2 = 0.f, s_mgmh = 0.f, s_gmg[3] = {0.f, 0.f, 0.f}, s_hmg[3] = {0.f, 0.f, 0.f};
+    for (int c = l8; c < C; c += 8) {
+        const float4 g = ldg_f4(Gm + (size_t)c * 4), h = ldg_f4(Hm + (size_t)c * 4);
+        s_mg2 = fmaf(g.x, g.x, s_mg2);
+        s_mgmh = fmaf(g.x, h.x, s_mgmh);
+        s_gmg[0] = fmaf(g.y, g.x, s_gmg[0]); s_gmg[1] = fmaf(g.z, g.x, s_gmg[1]); s_gmg[2] = fmaf(g.w, g.x, s_gmg[2]);
+        s_hmg[0] = fmaf(h.y, g.x, s_hmg[0]); s_hmg[1] = fmaf(h.z, g.x, s_hmg[1]); s_hmg[2] = fmaf(h.w, g.x, s_hmg[2]);
+    }
+    s_mg2 = group8_sum(s_mg2);
+    s_mgmh = group8_sum(s_mgmh);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { s_gmg[d] = group8_sum(s_gmg[d]); s_hmg[d] = group8_sum(s_hmg[d]); }
+    const float den_l = (s_mg2 + 1e-16f) + 1e-16f;
+    const float den_r = s_mgmh + 1e-16f;
+    float wl[3], wr[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { wl[d] = s_gmg[d] / den_l; wr[d] = s_hmg[d] / den_r; }
+    // forward, pass 2
+    float A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = l8; c < C; c += 8) {
+        const float4 g = ldg_f4(Gm + (size_t)c * 4), h = ldg_f4(Hm + (size_t)c * 4);
+        const float lf[3] = {fmaf(-wl[0], g.x, g.y), fmaf(-wl[1], g.x, g.z), fmaf(-wl[2], g.x, g.w)};
+        const float rt[3] = {fmaf(-wr[0], h.x, h.y), fmaf(-wr[1], h.x, h.z), fmaf(-wr[2], h.x, h.w)};
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) A[r * 3 + k] = fmaf(lf[r], rt[k], A[r * 3 + k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) A[k] = group8_sum(A[k]);
+    V3 L[3], Rr[3];
+    svd_frames(A, L, Rr);
+    float R[9];
+    rotation_from_frames(L, Rr, R);
+    // signed singular values s_i = l_i^T A r_i
+    float sv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const V3 Ar = {fmaf(A[0], Rr[i].x, fmaf(A[1], Rr[i].y, A[2] * Rr[i].z)), fmaf(A[3], Rr[i].x, fmaf(A[4], Rr[i].y, A[5] * Rr[i].z)),
+                       fmaf(A[6], Rr[i].x, fmaf(A[7], Rr[i].y, A[8] * Rr[i].z))};
+        sv[i] = dot(L[i], Ar);
+    }
+    // T[:3,:3] = R^T, T[:3,3] = b2 = wr - wl R
+    const float* gt = gT + (size_t)hc * 16;
+    float gR[9], gb[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) gb[j] = __ldg(gt + j * 4 + 3);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gR[r * 3 + k] = __ldg(gt + k * 4 + r) - wl[r] * gb[k];
+    float gwl[3], gwr[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        gwl[r] = -(gb[0] * R[r * 3 + 0] + gb[1] * R[r * 3 + 1] + gb[2] * R[r * 3 + 2]);
+        gwr[r] = gb[r];
+    }
+    // gZ = L^T gR Rr ; gP = antisymmetrised and divided ; gA = L gP Rr^T
+    float gZ[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        // row vector l_i^T gR
+        const float u0 = L[i].x * gR[0] + L[i].y * gR[3] + L[i].z * gR[6];
+        const float u1 = L[i].x * gR[1] + L[i].y * gR[4] + L[i].z * gR[7];
+        const float u2 = L[i].x * gR[2] + L[i].y * gR[5] + L[i].z * gR[8];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gZ[i * 3 + j] = u0 * Rr[j].x + u1 * Rr[j].y + u2 * Rr[j].z;
+    }
+    float gP[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float smax = fmaxf(fabsf(sv[0]), 1e-30f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 3; ++j) {
+            const float den = sv[i] + sv[j];
+            const float k = (fabsf(den) > 1e-7f * smax) ? (gZ[i * 3 + j] - gZ[j * 3 + i]) / den : 0.f;   // (rank <= 1: R is not unique)
+            gP[i * 3 + j] = k;
+            gP[j * 3 + i] = -k;
+        }
+    float gA[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float lr[3] = {r == 0 ? L[0].x : (r == 1 ? L[0].y : L[0].z), r == 0 ? L[1].x : (r == 1 ? L[1].y : L[1].z),
+                             r == 0 ? L[2].x : (r == 1 ? L[2].y : L[2].z)};
+        // row r of L gP
+        const float w0 = lr[0] * gP[0] + lr[1] * gP[3] + lr[2] * gP[6];
+        const float w1 = lr[0] * gP[1] + lr[1] * gP[4] + lr[2] * gP[7];
+        const float w2 = lr[0] * gP[2] + lr[1] * gP[5] + lr[2] * gP[8];
+        gA[r * 3 + 0] = w0 * Rr[0].x + w1 * Rr[1].x + w2 * Rr[2].x;
+        gA[r * 3 + 1] = w0 * Rr[0].y + w1 * Rr[1].y + w2 * Rr[2].y;
+        gA[r * 3 + 2] = w0 * Rr[0].z + w1 * Rr[1].z + w2 * Rr[2].z;
+    }
+    // pass 3: the centroid weights also collect  - sum_c mg_c g_left_c  and  - sum_c mh_c g_right_c
+    float t_l[3] = {0.f, 0.f, 0.f}, t_r[3] = {0.f, 0.f, 0.f};
+    for (int c = l8; c < C; c += 8) {
+        const float4 g = ldg_f4(Gm + (size_t)c * 4), h = ldg_f4(Hm + (size_t)c * 4);
+        const float lf[3] = {fmaf(-wl[0], g.x, g.y), fmaf(-wl[1], g.x, g.z), fmaf(-wl[2], g.x, g.w)};
+        const float rt[3] = {fmaf(-wr[0], h.x, h.y), fmaf(-wr[1], h.x, h.z), fmaf(-wr[2], h.x, h.w)};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float gl = gA[r * 3 + 0] * rt[0] + gA[r * 3 + 1] * rt[1] + gA[r * 3 + 2] * rt[2];      // g_left_c[r]
+            const float gr = gA[0 * 3 + r] * lf[0] + gA[1 * 3 + r] * lf[1] + gA[2 * 3 + r] * lf[2];      // g_right_c[r]
+            t_l[r] = fmaf(g.x, gl, t_l[r]);
+            t_r[r] = fmaf(h.x, gr, t_r[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { gwl[r] -= group8_sum(t_l[r]); gwr[r] -= group8_sum(t_r[r]); }
+    const float nl_gwl = s_gmg[0] * gwl[0] + s_gmg[1] * gwl[1] + s_gmg[2] * gwl[2];
+    const float nr_gwr = s_hmg[0] * gwr[0] + s_hmg[1] * gwr[1] + s_hmg[2] * gwr[2];
+    const float il = 1.f / den_l, ir = 1.f / den_r;
+    // pass 4: the rows' gradients
+    if (valid) {
+        for (int c = l8; c < C; c += 8) {
+            const float4 g = ldg_f4(Gm + (size_t)c * 4), h = ldg_f4(Hm + (size_t)c * 4);
+            const float lf[3] = {fmaf(-wl[0], g.x, g.y), fmaf(-wl[1], g.x, g.z), fmaf(-wl[2], g.x, g.w)};
+            const float rt[3] = {fmaf(-wr[0], h.x, h.y), fmaf(-wr[1], h.x, h.z), fmaf(-wr[2], h.x, h.w)};
+            float gl[3], gr[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                gl[r] = gA[r * 3 + 0] * rt[0] + gA[r * 3 + 1] * rt[1] + gA[r * 3 + 2] * rt[2];
+                gr[r] = gA[0 * 3 + r] * lf[0] + gA[1 * 3 + r] * lf[1] + gA[2 * 3 + r] * lf[2];
+            }
+            const float gv[3] = {g.y, g.z, g.w}, hv[3] = {h.y, h.z, h.w};
+            float g_mg = -2.f * g.x * nl_gwl * il * il - h.x * nr_gwr * ir * ir;
+            float g_mh = -g.x * nr_gwr * ir * ir;
+            float og[3], oh[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                g_mg += -gl[r] * wl[r] + gv[r] * gwl[r] * il + hv[r] * gwr[r] * ir;
+                g_mh += -gr[r] * wr[r];
+                og[r] = gl[r] + g.x * gwl[r] * il;
+                oh[r] = gr[r] + g.x * gwr[r] * ir;
+            }
+            *reinterpret_cast<float4*>(gG + ((size_t)hyp * C + c) * 4) = make_float4(g_mg, og[0], og[1], og[2]);
+            *reinterpret_cast<float4*>(gH + ((size_t)hyp * C + c) * 4) = make_float4(g_mh, oh[0], oh[1], oh[2]);
+        }
+    }
+}
+
 // utils/eval_utils.py:60-76: one thread per pair of rotations.
 __global__ void rotation_error_kernel(const float* __restrict__ R, const float* __restrict__ Rh, int64_t n, int sr, int sh,
                                       float* __restrict__ out) {
@@ -227,4 +395,22 @@ extern "C" int ume_rigid_solve_f32(const float* G, const float* H, const int64_t
     rigid_kernel<<<(unsigned)blocks, 256, 0, stream>>>(G, H, gi, hi, offG, offH, total, nG, nH, nm, C, T);
     count_launch();
     return check_launch("rigid_kernel");
+}
+
+extern "C" int ume_rigid_solve_backward_f32(const float* G, const float* H, const float* gT, int64_t nb, int C, float* gG,
+                                            float* gH, void* stream_) {
+    using namespace ume;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    UME_REQUIRE(nb >= 0, UME_ERR_BAD_ARG, "ume_rigid_solve_backward_f32: negative size");
+    if (nb == 0) return UME_OK;
+    UME_REQUIRE(G && H && gT && gG && gH, UME_ERR_BAD_ARG, "ume_rigid_solve_backward_f32: null pointer");
+    UME_REQUIRE(C >= 1, UME_ERR_BAD_ARG, "ume_rigid_solve_backward_f32: C must be >= 1");
+    UME_REQUIRE(reinterpret_cast<uintptr_t>(G) % 16 == 0 && reinterpret_cast<uintptr_t>(H) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(gG) % 16 == 0 && reinterpret_cast<uintptr_t>(gH) % 16 == 0,
+                UME_ERR_BAD_ARG, "ume_rigid_solve_backward_f32: pointers not 16-byte aligned");
+    const int64_t blocks = (nb + 31) / 32;
+    UME_REQUIRE(blocks < 0x7fffffffll, UME_ERR_UNSUPPORTED, "ume_rigid_solve_backward_f32: too many hypotheses");
+    rigid_backward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(G, H, gT, nb, C, gG, gH);
+    count_launch();
+    return check_launch("rigid_backward_kernel");
 }

@@ -9,9 +9,11 @@ What runs where:
     kernels; the moment build is a `torch.autograd.Function` whose backward is the scatter kernel
     `ume_moments_backward_f32`, so the reference's (bs, n, max_nn, C) gather tensor (2.6 GB at the
     shipped training config) exists neither in the forward nor in the backward pass;
-  * everything downstream of the (bs, n, C, 4) moment matrices — thin QR, projector distance,
-    3x3 SVD solve, soft-max losses — works on small per-keypoint matrices and is left to torch's
-    own differentiable ops (hand-written backward kernels for those are a later item).
+  * the projector distance (thin QR -> P = Q Q^T -> cdist) and the 3x3 SVD solve downstream of the
+    (bs, n, C, 4) moment matrices are `torch.autograd.Function`s too: forward = the inference kernels,
+    backward = `ume_cdist_backward_f32` / `ume_rigid_solve_backward_f32` (closed forms on the 4x4 Gram
+    blocks and on the proper singular frames of the 3x3 cross moment; no (bs,n,C,C) projector, no
+    cuSOLVER autograd).  Only the soft-max / mean reductions of the losses themselves are torch ops.
 """
 import numpy as np
 import torch
@@ -89,30 +91,51 @@ def generate_ume_from_keypoints2(velo_pts, velo_seg, velo_feat, ref_pts, ref_fea
     return F_velo, F_ref, velo_kp, ref_kp, ratio, has_kpts
 
 
+class _UmeCdist(torch.autograd.Function):
+    """D = ume_cdist(ume1, ume2) (utils/loc_utils.py:8-15) with a hand-written backward: the orthonormal bases
+    and the Gram-form distance kernel forward, `ume_cdist_backward_f32` (two GEMM-shaped passes over the 4x4
+    Gram blocks + a per-matrix triangular solve) backward.  Inputs must have full column rank (the loss
+    filters the others out, loss.py:76-88)."""
+
+    @staticmethod
+    def forward(ctx, ume1, ume2):
+        u1, u2 = ume1.detach().contiguous(), ume2.detach().contiguous()
+        Q1, Q2 = api.ume_descriptors(u1), api.ume_descriptors(u2)
+        D = api.descriptor_cdist(Q1, Q2, want_D=True)[0]
+        ctx.save_for_backward(u1, u2, Q1, Q2, D)
+        return D
+
+    @staticmethod
+    def backward(ctx, gD):
+        u1, u2, Q1, Q2, D = ctx.saved_tensors
+        return api.ume_cdist_backward(u1, u2, Q1, Q2, D, gD.detach().contiguous())
+
+
+class _RigidFromUme(torch.autograd.Function):
+    """T = batch_estimate_transform_ume_old(G, H)[0] (utils/loc_utils.py:292-335) with a hand-written backward
+    (`ume_rigid_solve_backward_f32`)."""
+
+    @staticmethod
+    def forward(ctx, G, H):
+        g, h = G.detach().contiguous(), H.detach().contiguous()
+        ctx.save_for_backward(g, h)
+        return api.rigid_solve(g[None], h[None])[0]
+
+    @staticmethod
+    def backward(ctx, gT):
+        g, h = ctx.saved_tensors
+        return api.rigid_solve_backward(g, h, gT.detach().contiguous())
+
+
 def ume_cdist_autograd(ume1, ume2):
-    """utils/loc_utils.py:8-15 with torch's differentiable QR / cdist (small matrices)."""
-    Q1 = torch.linalg.qr(ume1, mode="reduced").Q
-    Q2 = torch.linalg.qr(ume2, mode="reduced").Q
-    P1, P2 = Q1 @ Q1.transpose(-1, -2), Q2 @ Q2.transpose(-1, -2)
-    return torch.cdist(P1.flatten(2), P2.flatten(2)) / np.sqrt(2)
+    """Differentiable utils/loc_utils.py:8-15: (bs,n1,C,4) x (bs,n2,C,4) -> D (bs,n1,n2)."""
+    return _UmeCdist.apply(ume1, ume2)
 
 
 def rigid_from_ume_autograd(G, H):
-    """The (R,t) part of utils/loc_utils.py:292-335 as differentiable torch ops: G, H (B',C,4) ->
-    T (B',4,4) with T[:3,:3] = R^T, T[:3,3] = b2."""
-    mg, mh, g, h = G[:, :, :1], H[:, :, :1], G[:, :, 1:], H[:, :, 1:]
-    wl = (g * mg).sum(1, keepdim=True) / ((mg * mg).sum(1, keepdim=True) + 2e-16)
-    wr = (h * mg).sum(1, keepdim=True) / ((mg * mh).sum(1, keepdim=True) + 1e-16)
-    left, right = g - wl * mg, h - wr * mh
-    U, _, Vh = torch.linalg.svd(left.transpose(1, 2) @ right)
-    fix = torch.ones(G.shape[0], 3, device=G.device, dtype=G.dtype)
-    fix[:, 2] = torch.sign(torch.det(U @ Vh))
-    R = (U * fix[:, None, :]) @ Vh
-    b2 = wr - wl @ R
-    T = torch.eye(4, device=G.device, dtype=G.dtype).repeat(G.shape[0], 1, 1)
-    T[:, :3, :3] = R.transpose(1, 2)
-    T[:, :3, 3] = b2[:, 0]
-    return T
+    """Differentiable (R,t) part of utils/loc_utils.py:292-335: G, H (B',C,4) -> T (B',4,4) with T[:3,:3] = R^T,
+    T[:3,3] = b2."""
+    return _RigidFromUme.apply(G, H)
 
 
 class UMEContrastiveLoss(torch.nn.Module):
