@@ -84,6 +84,15 @@ int ume_moments_f32(const float* pts, const float* kpts, const float* feat, int 
                     int C, int K, float radius, unsigned flags, float* F, float* Fc, int32_t* count,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* The source and the target batch of a registration step (evaluate.py:206-207 calls my_ume_generation twice) in ONE
+ * search-grid build and ONE moment launch.  pts1/kpts1/feat1 and pts2/kpts2/feat2 as in ume_moments_f32, the same
+ * B, N, n, C on both sides; F, Fc (may be NULL), count (may be NULL) hold 2B clouds: [0,B) side 1, [B,2B) side 2.
+ * Results are bit-identical to two ume_moments_f32 calls.  C in {16,32,64,128}; workspace:
+ * ume_moments_workspace_bytes(2B, N, n, C, K). */
+int ume_moments_pair_f32(const float* pts1, const float* kpts1, const float* feat1, const float* pts2, const float* kpts2,
+                         const float* feat2, int B, int N, int n, int C, int K, float radius, unsigned flags, float* F,
+                         float* Fc, int32_t* count, void* ws, size_t ws_bytes, void* stream);
+
 /* Gradient of the RAW moments with respect to the features (the backward pass of the
  * training-time UME generation, utils/loc_utils.py:86-188, which the reference gets from autograd
  * through its materialised (B,n,K,C) gather):

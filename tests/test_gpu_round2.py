@@ -390,3 +390,39 @@ def test_cdist_presplit_operands_equal_the_generic_entry(ume, C, B, n1, n2):
     q = host(Qt1).astype(np.float64) * 256.0
     h = host(Qh1).astype(np.float64)
     assert np.abs(h[..., :C] + h[..., C:] - q).max() < 256.0 * 2.0 ** -21
+
+
+# ----------------------------------------------------------------------------- source + target in one launch
+@pytest.mark.parametrize("C,n", [(32, 1600), (64, 1550)])
+def test_pair_launch_is_bit_identical_to_two_launches(ume, C, n):
+    """`ume_moments_pair_f32` (one grid build, one moment launch for 2B clouds) against two `ume_moments_f32` calls:
+    the cell-sorted arrays are a pure function of each cloud, so F and Fc must agree bit for bit; and the registration
+    step built on it returns exactly what the two-launch step returns."""
+    b = synth.make_batch(2, seed0=5, n_base=2, N=30000, C=C, n_kp=n)
+    d = {k: dev(v) for k, v in b.items() if k.endswith(("pts", "feat", "kp"))}
+    ume.config["warp_moments"] = True
+    try:
+        F1, Fc1 = ume.ume_moments(d["src_pts"], d["src_kp"], d["src_feat"], 750, 5.0, return_centered=True)
+        F2, Fc2 = ume.ume_moments(d["tgt_pts"], d["tgt_kp"], d["tgt_feat"], 750, 5.0, return_centered=True)
+    finally:
+        ume.config["warp_moments"] = False
+    pair = ume.ume_moments_pair(d["src_pts"], d["src_kp"], d["src_feat"], d["tgt_pts"], d["tgt_kp"], d["tgt_feat"], 750, 5.0,
+                                return_centered=True)
+    assert pair is not None
+    G1, Gc1, G2, Gc2, both = pair
+    assert torch.equal(G1, F1) and torch.equal(Gc1, Fc1) and torch.equal(G2, F2) and torch.equal(Gc2, Fc2)
+    assert both.shape[0] == 4 and both.data_ptr() == Gc1.data_ptr()
+    # different shapes on the two sides: the pair entry declines, the step falls back to two launches
+    assert ume.ume_moments_pair(d["src_pts"], d["src_kp"], d["src_feat"], d["tgt_pts"][:, :-8], d["tgt_kp"], d["tgt_feat"][:, :-8],
+                                750, 5.0) is None
+    out = ume.register_hypotheses(d["src_pts"], d["src_feat"], d["src_kp"], d["tgt_pts"], d["tgt_feat"], d["tgt_kp"], 750, 5.0, want_D=True)
+    ume.config["cta_moments"] = True             # the pair entry declines: two launches of the CTA kernel
+    try:
+        ref = ume.register_hypotheses(d["src_pts"], d["src_feat"], d["src_kp"], d["tgt_pts"], d["tgt_feat"], d["tgt_kp"], 750, 5.0, want_D=True)
+    finally:
+        ume.config["cta_moments"] = False
+    # (the CTA kernel sums in another order: the distances agree to the Gram form's rounding, the matches wherever
+    # the distance gap is clear)
+    assert float((out["D"] - ref["D"]).abs().max()) < 2e-3
+    same = (out["match"][..., 1] == ref["match"][..., 1]).float().mean()
+    assert float(same) > 0.99

@@ -6,7 +6,8 @@ descriptor-and-registration hot path, behind the reference's own Python call sig
 
 See DESIGN.md for the path and its boundary, include/umereg_b200.h for the C ABI.
 """
-from .api import (ball_query, knn_points, knn_gather, knn1_transfer, ume_moments, ume_moments_backward,
+from .api import (ball_query, knn_points, knn_gather, knn1_transfer, ume_moments, ume_moments_pair, ume_moments_backward,
+                  rigid_solve_backward, ume_cdist_backward,
                   neighbor_count, my_ume_generation,
                   create_local_ume_matrix, ume_descriptors, ume_descriptors_split, descriptor_cdist, descriptor_cdist_split, ume_cdist, rigid_solve,
                   batch_estimate_transform_ume_old, relative_rotation_error, ball_query_gather, ume_kp_layer,
@@ -15,7 +16,8 @@ from .api import (ball_query, knn_points, knn_gather, knn1_transfer, ume_moments
                   select_hypothesis, linear_sum_assignment, hungarian_match, config)
 from .patch import patch_reference
 
-__all__ = ["ball_query", "knn_points", "knn_gather", "knn1_transfer", "ume_moments", "ume_moments_backward",
+__all__ = ["ball_query", "knn_points", "knn_gather", "knn1_transfer", "ume_moments", "ume_moments_pair", "ume_moments_backward",
+           "rigid_solve_backward", "ume_cdist_backward",
            "neighbor_count", "my_ume_generation",
            "create_local_ume_matrix", "ume_descriptors", "ume_descriptors_split", "descriptor_cdist", "descriptor_cdist_split", "ume_cdist", "rigid_solve",
            "batch_estimate_transform_ume_old", "relative_rotation_error", "ball_query_gather", "ume_kp_layer",

@@ -87,6 +87,7 @@ def _bind(lib):
         "ume_ball_query_f32": (i32, [vp, vp, i32, i32, i32, i32, f32, u32, vp, vp, vp, vp, vp, sz, vp]),
         "ume_moments_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
         "ume_moments_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, u32, vp, vp, vp, vp, sz, vp]),
+        "ume_moments_pair_f32": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, u32, vp, vp, vp, vp, sz, vp]),
         "ume_moments_backward_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, u32, vp, vp, sz, vp]),
         "ume_neighbor_count_f32": (i32, [vp, vp, i32, i32, i32, i32, f32, u32, vp, vp, sz, vp]),
         "ume_orthonormalize_f32": (i32, [vp, i64, i32, vp, vp, vp]),
@@ -132,7 +133,8 @@ EXPORTED_SYMBOLS = ["ume_abi_version", "ume_last_error", "ume_status_string", "u
                     "ume_voxel_unique_workspace_bytes", "ume_voxel_unique_f32",
                     "ume_moments_backward_f32", "ume_neighbor_count_f32", "ume_linear_sum_assignment_host_f32",
                     "ume_rotation_error_deg_f32", "ume_gumbel_topk_f32", "ume_orthonormalize_split_f32", "ume_cdist_split_f16",
-                    "ume_rigid_solve_backward_f32", "ume_cdist_backward_workspace_bytes", "ume_cdist_backward_f32"]
+                    "ume_rigid_solve_backward_f32", "ume_cdist_backward_workspace_bytes", "ume_cdist_backward_f32",
+                    "ume_moments_pair_f32"]
 
 
 def lib():

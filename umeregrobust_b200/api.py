@@ -236,6 +236,37 @@ def ume_moments(pts, kpts, feat, K, radius, return_centered=False, return_count=
     return out[0] if len(out) == 1 else out
 
 
+WARP_KERNEL_MIN_KEYPOINTS = 3072      # below this a launch is faster on the CTA-per-keypoint kernel (csrc/moments.cu)
+
+
+def ume_moments_pair(pts1, kpts1, feat1, pts2, kpts2, feat2, K, radius, return_centered=False, buf=None):
+    """`ume_moments` of a source and a target batch in ONE search-grid build and ONE kernel launch
+    (`ume_moments_pair_f32`): returns (F1, F2, F_both) or (F1, Fc1, F2, Fc2, Fc_both) — the per-side results are
+    the halves of one (2B,n,C,4) allocation (the last element), bit-identical to two `ume_moments` calls.  Returns None when the pair entry does not apply (different
+    shapes on the two sides, a channel count or a launch size the warp-per-keypoint kernel is not used for)."""
+    if config["cta_moments"] is True or tuple(pts1.shape) != tuple(pts2.shape) or tuple(kpts1.shape) != tuple(kpts2.shape) \
+            or tuple(feat1.shape) != tuple(feat2.shape) or feat1.dim() != 3:
+        return None
+    B, N, _ = pts1.shape
+    n, C = kpts1.shape[1], feat1.shape[2]
+    if C not in (16, 32, 64, 128) or (2 * B * n < WARP_KERNEL_MIN_KEYPOINTS and not config.get("warp_moments")) or 2 * B > 65535:
+        return None
+    pts1, kpts1, feat1 = _dev_f32(pts1, "pts1", 3), _dev_f32(kpts1, "kpts1", 3), _dev_f32(feat1, "feat1", 3)
+    pts2, kpts2, feat2 = _dev_f32(pts2, "pts2", 3), _dev_f32(kpts2, "kpts2", 3), _dev_f32(feat2, "feat2", 3)
+    dev = pts1.device
+    F = _out(buf, "F_pair", (2 * B, n, C, 4), torch.float32, dev)
+    Fc = _out(buf, "Fc_pair", (2 * B, n, C, 4), torch.float32, dev) if return_centered else None
+    with torch.cuda.device(dev):
+        L = _lib.lib()
+        ws = _workspace(L.ume_moments_workspace_bytes(2 * B, N, n, C, int(K)), dev, buf)
+        rc = L.ume_moments_pair_f32(_ptr(pts1), _ptr(kpts1), _ptr(feat1), _ptr(pts2), _ptr(kpts2), _ptr(feat2), B, N, n, C,
+                                    int(K), float(radius), _flags(), _ptr(F), _ptr(Fc), None, _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "ume_moments_pair")
+    if return_centered:
+        return F[:B], Fc[:B], F[B:], Fc[B:], Fc
+    return F[:B], F[B:], F
+
+
 def ume_moments_backward(pts, kpts, grad_F, K, radius):
     """Gradient of the RAW moments with respect to the features: the same
     neighbourhoods as `ume_moments(pts, kpts, ., K, radius)`, every neighbour row j of keypoint i
@@ -803,21 +834,35 @@ def register_hypotheses(src_pts, src_feat, src_kp, tgt_pts, tgt_feat, tgt_kp, K,
     m of the n matches drawn without replacement with probability ~ exp((1 - d)/tau) on the device
     (`weighted_match_subsample`); match / dmin / T then have m rows per pair.
     Returns dict(F_src, F_tgt, match (B,n,2) int64, dmin (B,n), T (B,n,4,4), D or None)."""
+    # both sides in one grid build and one moment launch where the pair entry applies (same shapes, warp kernel)
+    pair = ume_moments_pair(src_pts, src_kp, src_feat, tgt_pts, tgt_kp, tgt_feat, K, radius, return_centered=centered, buf=buf)
     if centered:
-        F_src, Fc_src = ume_moments(src_pts, src_kp, src_feat, K, radius, return_centered=True, buf=buf, tag="_src")
-        F_tgt, Fc_tgt = ume_moments(tgt_pts, tgt_kp, tgt_feat, K, radius, return_centered=True, buf=buf, tag="_tgt")
+        if pair is not None:
+            F_src, Fc_src, F_tgt, Fc_tgt, both = pair
+        else:
+            F_src, Fc_src = ume_moments(src_pts, src_kp, src_feat, K, radius, return_centered=True, buf=buf, tag="_src")
+            F_tgt, Fc_tgt = ume_moments(tgt_pts, tgt_kp, tgt_feat, K, radius, return_centered=True, buf=buf, tag="_tgt")
         A, Bm = Fc_src, Fc_tgt
     else:
-        F_src = ume_moments(src_pts, src_kp, src_feat, K, radius, buf=buf, tag="_src")
-        F_tgt = ume_moments(tgt_pts, tgt_kp, tgt_feat, K, radius, buf=buf, tag="_tgt")
+        if pair is not None:
+            F_src, F_tgt, both = pair
+        else:
+            F_src = ume_moments(src_pts, src_kp, src_feat, K, radius, buf=buf, tag="_src")
+            F_tgt = ume_moments(tgt_pts, tgt_kp, tgt_feat, K, radius, buf=buf, tag="_tgt")
         A, Bm = F_src, F_tgt
     if matching not in ("argmin", "hungarian"):
         raise ValueError("register_hypotheses: matching must be 'argmin' or 'hungarian'")
     C = A.shape[-2]
     if C in (32, 64) and config["cdist_impl"] in (None, 1):
         # tensor-core distance kernel, operands written pre-split by the orthonormalisation kernel
-        D, am, dm = descriptor_cdist_split(ume_descriptors_split(A, buf=buf, tag="_src"), ume_descriptors_split(Bm, buf=buf, tag="_tgt"),
-                                           want_D=want_D or matching == "hungarian", want_argmin=True, buf=buf)
+        if pair is not None:
+            # (the two sides are halves of one allocation: one orthonormalisation launch for both)
+            nb = A.shape[0]
+            Qh = ume_descriptors_split(both, buf=buf, tag="_pair")
+            Qh_src, Qh_tgt = Qh[:nb], Qh[nb:]
+        else:
+            Qh_src, Qh_tgt = ume_descriptors_split(A, buf=buf, tag="_src"), ume_descriptors_split(Bm, buf=buf, tag="_tgt")
+        D, am, dm = descriptor_cdist_split(Qh_src, Qh_tgt, want_D=want_D or matching == "hungarian", want_argmin=True, buf=buf)
     else:
         D, am, dm = descriptor_cdist(ume_descriptors(A, buf=buf, tag="_src"), ume_descriptors(Bm, buf=buf, tag="_tgt"),
                                      want_D=want_D or matching == "hungarian", want_argmin=True, buf=buf)

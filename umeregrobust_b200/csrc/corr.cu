@@ -175,6 +175,8 @@ __global__ void __launch_bounds__(128) knn_kernel(GridView grid, const float* __
     top.reset(K);
     grid_knn<kFma>(h, cs, sorted_b, q[qo * 3 + 0], q[qo * 3 + 1], q[qo * 3 + 2], top);
     for (int k = 0; k < K; ++k) {
+        // fewer than K usable rows: padded with index 0 / distance 0, as pytorch3d's knn_points pads (its outputs are
+        // zero-initialised); callers mask by the row count
         if (idx) idx[qo * K + k] = (k < top.n) ? top.bj[k] : 0;
         if (d2) d2[qo * K + k] = (k < top.n) ? top.bd[k] : 0.f;
     }
@@ -211,7 +213,8 @@ __global__ void __launch_bounds__(128) spatial_var_kernel(GridView grid, const f
         }
         acc += sqrtf(s);
     }
-    out[(size_t)b * N + i] = (K > 1) ? acc / (float)(K - 1) : 0.f;
+    // (rows with non-finite coordinates are not in the grid: with fewer than K usable rows the mean is over what was found)
+    out[(size_t)b * N + i] = (top.n > 1) ? acc / (float)(top.n - 1) : 0.f;
 }
 
 // ---------------------------------------------------------------- weighted features
@@ -241,6 +244,12 @@ struct CorrParams {
     float inv_sigma;
 };
 
+#ifndef UME_CORR_TGT_PPC
+#define UME_CORR_TGT_PPC(K) ((float)max(2, (K) / 8))   // target points per grid cell the ring search walks
+#endif
+#ifndef UME_CORR_SRC_PPC
+#define UME_CORR_SRC_PPC 8.f                            // source points per cell: the CTA's queries are neighbours
+#endif
 #ifndef UME_CORR_MINB
 #define UME_CORR_MINB 6            // CTAs per SM the register allocation is capped for
 #endif
@@ -420,7 +429,8 @@ extern "C" int ume_feature_spatial_var_f32(const float* pts, const float* feat, 
     int rc = grid_build(pts, pts, B, N, N, 0.f, -(float)max(2, knn / 8), kCellsCap, w, &g, stream);
     if (rc != UME_OK) return rc;
     ProfScope prof(UME_PROF_KNN, stream);
-    cudaMemsetAsync(out, 0, (size_t)B * N * sizeof(float), stream);      // rows with non-finite coordinates
+    cudaError_t me = cudaMemsetAsync(out, 0, (size_t)B * N * sizeof(float), stream);      // rows with non-finite coordinates
+    UME_REQUIRE(me == cudaSuccess, UME_ERR_CUDA, "ume_feature_spatial_var_f32: cudaMemsetAsync: %s", cudaGetErrorString(me));
     dim3 grid((unsigned)((N + 127) / 128), (unsigned)B);
     const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
     if (fma) spatial_var_kernel<64, true><<<grid, 128, 0, stream>>>(g, feat, C, knn, out);
@@ -466,9 +476,9 @@ extern "C" int ume_corr_scores_f32(const float* src_pts, const float* tgt_pts, c
                 "ume_corr_scores_f32: workspace too small");
     Workspace w(ws, ws_bytes);
     CorrParams p;
-    int rc = grid_build(src_pts, src_pts, 1, Ns, Ns, 0.f, -8.f, kCellsCap, w, &p.src_grid, stream);
+    int rc = grid_build(src_pts, src_pts, 1, Ns, Ns, 0.f, -UME_CORR_SRC_PPC, kCellsCap, w, &p.src_grid, stream);
     if (rc != UME_OK) return rc;
-    rc = grid_build(tgt_pts, tgt_pts, 1, Nt, Nt, 0.f, -(float)max(2, K / 8), kCellsCap, w, &p.tgt_grid, stream);
+    rc = grid_build(tgt_pts, tgt_pts, 1, Nt, Nt, 0.f, -UME_CORR_TGT_PPC(K), kCellsCap, w, &p.tgt_grid, stream);
     if (rc != UME_OK) return rc;
     const int nb = (Ns + kCorrThreads - 1) / kCorrThreads;
     p.partial = w.take<float>((size_t)n_hyp * nb);

@@ -19,9 +19,15 @@ __global__ void grid_init_kernel(int* __restrict__ bbox, int B) {
     if (i < B * 6) bbox[i] = (i % 6 < 3) ? INT_MAX : INT_MIN;   // [min xyz | max xyz] as ordered keys
 }
 
-__global__ void grid_bbox_kernel(const float* __restrict__ q, int nq, int* __restrict__ bbox) {
+// clouds [0, Bs) come from the first array, clouds [Bs, B) from the second one (a source / target pair of batches
+// handled by ONE launch; Bs = B and a null second array for a single batch)
+UME_DEVI const float* cloud_of(const float* a, const float* a2, int Bs, int b, size_t stride) {
+    return (b < Bs) ? a + (size_t)b * stride : a2 + (size_t)(b - Bs) * stride;
+}
+
+__global__ void grid_bbox_kernel(const float* __restrict__ q, const float* __restrict__ q2, int Bs, int nq, int* __restrict__ bbox) {
     const int b = blockIdx.y;
-    const float* qb = q + (size_t)b * nq * 3;
+    const float* qb = cloud_of(q, q2, Bs, b, (size_t)nq * 3);
     int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
         float x = qb[i * 3 + 0], y = qb[i * 3 + 1], z = qb[i * 3 + 2];
@@ -153,6 +159,9 @@ constexpr int kRankThreads = 512;
 // slices per cloud: about four CTAs per SM in total, at least ~2048 rows per slice
 static int grid_slices(int B, int N) {
     int G = (4 * 148) / (B > 0 ? B : 1);
+    // ... and at most ~14k rows per slice: the slice's shared-memory footprint (CTAs per SM) and the in-cell
+    // ranking pass (quadratic in the slice's rows per cell) grow with the slice
+    if (G < (N + 13999) / 14000) G = (N + 13999) / 14000;
     const int cap = N / 2048 < 64 ? N / 2048 : 64;
     if (G > cap) G = cap;
     const int need = (N + 65534) / 65535;                    // slice-local row numbers are 16 bits wide
@@ -161,8 +170,9 @@ static int grid_slices(int B, int N) {
 }
 
 __global__ void __launch_bounds__(kRankThreads)
-grid_rank_kernel(const float* __restrict__ pts, int N, int per, const GridHeader* __restrict__ hdr,
-                 int* __restrict__ slice_cnt, int cells_cap, int* __restrict__ cell_of, int* __restrict__ rank_of) {
+grid_rank_kernel(const float* __restrict__ pts, const float* __restrict__ pts2, int Bs, int N, int per,
+                 const GridHeader* __restrict__ hdr, int* __restrict__ slice_cnt, int cells_cap, int* __restrict__ cell_of,
+                 int* __restrict__ rank_of) {
     // 16-bit shared memory throughout (a slice holds < 65536 rows): cells_cap + 2 per-cell counters — bumped
     // two to a 32-bit word by the atomics, then turned in place into exclusive starts — and `per` slots
     // for the slice's row numbers grouped by cell.  43 KB at the usual sizes: four CTAs per SM.
@@ -175,7 +185,7 @@ grid_rank_kernel(const float* __restrict__ pts, int N, int per, const GridHeader
     const GridHeader h = hdr[b];
     const int ncells = h.ncells;
     const int lo = min(N, g * per), hi = min(N, lo + per);
-    const float* pb = pts + (size_t)b * N * 3;
+    const float* pb = cloud_of(pts, pts2, Bs, b, (size_t)N * 3);
     int* cell_b = cell_of + (size_t)b * N;
     int* rank_b = rank_of + (size_t)b * N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -284,11 +294,12 @@ __global__ void __launch_bounds__(1024) grid_scan_kernel(int* __restrict__ slice
     }
 }
 
-__global__ void grid_scatter_kernel(const float* __restrict__ pts, int N, int per, int G, const int* __restrict__ slice_base,
+__global__ void grid_scatter_kernel(const float* __restrict__ pts, const float* __restrict__ pts2, int Bs, int N, int per, int G,
+                                    const int* __restrict__ slice_base,
                                     int cells_cap, const int* __restrict__ cell_of, const int* __restrict__ rank_of,
                                     float4* __restrict__ sorted) {
     const int b = blockIdx.y;
-    const float* pb = pts + (size_t)b * N * 3;
+    const float* pb = cloud_of(pts, pts2, Bs, b, (size_t)N * 3);
     const int* tab = slice_base + (size_t)b * G * cells_cap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const int c = cell_of[(size_t)b * N + i];
@@ -314,7 +325,9 @@ size_t grid_workspace_bytes(int B, int N, int cells_cap) {
 }
 
 int grid_build(const float* pts, const float* q, int B, int N, int nq, float expand, float cell,
-               int cells_cap, Workspace& ws, GridView* view, cudaStream_t stream) {
+               int cells_cap, Workspace& ws, GridView* view, cudaStream_t stream, const float* pts2, const float* q2, int B2) {
+    const int Bs = B;                         // clouds [0, Bs) from (pts, q), clouds [Bs, Bs + B2) from (pts2, q2)
+    B += (pts2 != nullptr) ? B2 : 0;
     const int G = grid_slices(B, N);
     const int per = (N + G - 1) / G;
     GridHeader* hdr = ws.take<GridHeader>(B);
@@ -335,14 +348,14 @@ int grid_build(const float* pts, const float* q, int B, int N, int nq, float exp
     grid_init_kernel<<<(B * 6 + 127) / 128, 128, 0, stream>>>(bbox, B);
     if (nq > 0) {
         dim3 g((unsigned)min((nq + 255) / 256, 64), (unsigned)B);
-        grid_bbox_kernel<<<g, 256, 0, stream>>>(q, nq, bbox);
+        grid_bbox_kernel<<<g, 256, 0, stream>>>(q, q2, Bs, nq, bbox);
     }
     grid_params_kernel<<<(B + 127) / 128, 128, 0, stream>>>(bbox, hdr, B, expand, cell, cells_cap, N);
-    grid_rank_kernel<<<dim3((unsigned)G, (unsigned)B), kRankThreads, smem, stream>>>(pts, N, per, hdr, slice_cnt, cells_cap,
+    grid_rank_kernel<<<dim3((unsigned)G, (unsigned)B), kRankThreads, smem, stream>>>(pts, pts2, Bs, N, per, hdr, slice_cnt, cells_cap,
                                                                                    cell_of, rank_of);
     grid_scan_kernel<<<B, 1024, 0, stream>>>(slice_cnt, G, cell_start, hdr, cells_cap);
     dim3 gs((unsigned)min((N + 255) / 256, 296), (unsigned)B);
-    grid_scatter_kernel<<<gs, 256, 0, stream>>>(pts, N, per, G, slice_cnt, cells_cap, cell_of, rank_of, sorted);
+    grid_scatter_kernel<<<gs, 256, 0, stream>>>(pts, pts2, Bs, N, per, G, slice_cnt, cells_cap, cell_of, rank_of, sorted);
     count_launch(nq > 0 ? 6 : 5);
     view->hdr = hdr;
     view->cell_start = cell_start;

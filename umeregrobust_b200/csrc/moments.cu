@@ -303,6 +303,7 @@ extern "C" int ume_moments_f32(const float* pts, const float* kpts, const float*
         // one warp per keypoint (moments_warp.cuh): the default for the channel counts it is built for
         warpk::Params wp;
         wp.grid = p.grid; wp.kpts = kpts; wp.feat = feat; wp.F = F; wp.Fc = Fc; wp.count = count;
+        wp.kpts2 = nullptr; wp.feat2 = nullptr; wp.Bs = B;
         wp.gF = nullptr; wp.grad_feat = nullptr; wp.raw = raw ? 1 : 0;
         wp.n = n; wp.K = K; wp.total = (long long)B * n; wp.radius = radius;
         wp.next = w.take<unsigned long long>(1);
@@ -328,6 +329,41 @@ extern "C" int ume_moments_f32(const float* pts, const float* kpts, const float*
     return launch_moments<GenAcc<8>>(p, B, fma, stream);
 }
 
+// Source and target batch of a registration step in ONE grid build and ONE moment launch: 2B clouds, no tail
+// between the two sides, half the launches.  Warp-per-keypoint kernel only.
+extern "C" int ume_moments_pair_f32(const float* pts1, const float* kpts1, const float* feat1, const float* pts2,
+                                    const float* kpts2, const float* feat2, int B, int N, int n, int C, int K, float radius,
+                                    unsigned flags, float* F, float* Fc, int32_t* count, void* ws, size_t ws_bytes,
+                                    void* stream_) {
+    using namespace ume;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    UME_REQUIRE(B >= 0 && N >= 0 && n >= 0, UME_ERR_BAD_ARG, "ume_moments_pair_f32: negative size");
+    if (B == 0 || n == 0) return UME_OK;
+    UME_REQUIRE(pts1 && kpts1 && feat1 && pts2 && kpts2 && feat2 && F, UME_ERR_BAD_ARG, "ume_moments_pair_f32: null pointer");
+    UME_REQUIRE(N >= 1 && K >= 1, UME_ERR_BAD_ARG, "ume_moments_pair_f32: N = %d, K = %d", N, K);
+    UME_REQUIRE(N <= kMaxPoints && (size_t)2 * B * n < 0x7fffffffull && 2 * B <= 65535, UME_ERR_UNSUPPORTED,
+                "ume_moments_pair_f32: size not supported");
+    UME_REQUIRE((C == 16 || C == 32 || C == 64 || C == 128) && reinterpret_cast<uintptr_t>(feat1) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(feat2) % 16 == 0,
+                UME_ERR_UNSUPPORTED, "ume_moments_pair_f32: C = %d must be 16, 32, 64 or 128 (16-byte aligned rows)", C);
+    UME_REQUIRE(ws && ws_bytes >= ume_moments_workspace_bytes(2 * B, N, n, C, K), UME_ERR_WORKSPACE,
+                "ume_moments_pair_f32: workspace too small (%zu needed, %zu given)", ume_moments_workspace_bytes(2 * B, N, n, C, K),
+                ws_bytes);
+    Workspace w(ws, ws_bytes);
+    warpk::Params wp;
+    int rc = grid_build(pts1, kpts1, B, N, n, fabsf(radius), fabsf(radius) / (float)UME_WARPK_CELL_DIV, kCellsCap, w, &wp.grid,
+                        stream, pts2, kpts2, B);
+    if (rc != UME_OK) return rc;
+    wp.kpts = kpts1; wp.feat = feat1; wp.kpts2 = kpts2; wp.feat2 = feat2; wp.Bs = B;
+    wp.F = F; wp.Fc = Fc; wp.count = count;
+    wp.gF = nullptr; wp.grad_feat = nullptr; wp.raw = (flags & UME_FLAG_RAW_MOMENTS) ? 1 : 0;
+    wp.n = n; wp.K = K; wp.total = (long long)2 * B * n; wp.radius = radius;
+    wp.next = w.take<unsigned long long>(1);
+    UME_REQUIRE(w.ok(), UME_ERR_WORKSPACE, "ume_moments_pair_f32: workspace too small for the work counter");
+    ProfScope prof(UME_PROF_MOMENTS, stream);
+    return warpk::launch_c<warpk::kForward>(wp, C, (flags & UME_FLAG_FMA_DIST) != 0, stream);
+}
+
 // Shared front end of the two auxiliary entry points below (same checks and grid as ume_moments_f32).
 static int moments_aux(const float* pts, const float* kpts, const float* gF, int B, int N, int n, int C, int K,
                        float radius, unsigned flags, float* grad_feat, int32_t* count, void* ws, size_t ws_bytes,
@@ -345,6 +381,7 @@ static int moments_aux(const float* pts, const float* kpts, const float* gF, int
     int rc = grid_build(pts, kpts, B, N, n, fabsf(radius), fabsf(radius) / (float)UME_WARPK_CELL_DIV, kCellsCap, w, &wp.grid, stream);
     if (rc != UME_OK) return rc;
     wp.kpts = kpts; wp.feat = nullptr; wp.F = nullptr; wp.Fc = nullptr; wp.count = count;
+    wp.kpts2 = nullptr; wp.feat2 = nullptr; wp.Bs = B;
     wp.gF = gF; wp.grad_feat = grad_feat; wp.raw = 1;
     wp.n = n; wp.K = K; wp.total = (long long)B * n; wp.radius = radius;
     wp.next = w.take<unsigned long long>(1);

@@ -72,6 +72,9 @@ struct Params {
     GridView grid;
     const float* kpts;    // (B,n,3)
     const float* feat;    // (B,N,C)
+    const float* kpts2;   // clouds [Bs, B): keypoints / features of a second batch handled by the same launch
+    const float* feat2;   //   (null and Bs = B for a single batch); F, Fc, count cover all B clouds
+    int Bs;
     float* F;             // (B,n,C,4)
     float* Fc;            // (B,n,C,4) or null
     int32_t* count;       // (B,n) or null
@@ -202,8 +205,9 @@ __global__ void __launch_bounds__(32 * kWarps, UME_WARPK_MINB) moments_warp_kern
     const GridHeader h = p.grid.hdr[b];
     const int* cs = p.grid.cell_start + (size_t)b * (p.grid.cells_cap + 1);
     const float4* sorted_b = p.grid.sorted + (size_t)b * N;
-    const float* feat_b = p.feat + (size_t)b * N * C;
-    const float kx = p.kpts[q * 3 + 0], ky = p.kpts[q * 3 + 1], kz = p.kpts[q * 3 + 2];
+    const float* feat_b = (b < p.Bs) ? p.feat + (size_t)b * N * C : p.feat2 + (size_t)(b - p.Bs) * N * C;
+    const float* kp = (b < p.Bs) ? p.kpts + q * 3 : p.kpts2 + (q - (unsigned long long)p.Bs * p.n) * 3;
+    const float kx = kp[0], ky = kp[1], kz = kp[2];
     const float r2 = __fmul_rn(p.radius, p.radius);
     const int K = p.K;
 

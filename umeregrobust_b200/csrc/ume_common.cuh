@@ -117,9 +117,11 @@ UME_DEVI unsigned lanemask_lt() {
 size_t grid_workspace_bytes(int B, int N, int cells_cap);
 // Builds the grid for clouds `pts` (B,N,3) over the bounding box of `q` (B,nq,3) grown by
 // `expand`; cell size `cell` (0: the finest the table allows; < 0: about -cell points per cell for
-// a surface-like cloud).  Carves its buffers out of `ws` and fills `view`.
+// a surface-like cloud).  Carves its buffers out of `ws` and fills `view`.  With (pts2, q2, B2) the grids of a
+// second batch of B2 clouds (same N, nq) are built by the same launches: clouds [B, B + B2) of the view.
 int grid_build(const float* pts, const float* q, int B, int N, int nq, float expand, float cell,
-               int cells_cap, Workspace& ws, GridView* view, cudaStream_t stream);
+               int cells_cap, Workspace& ws, GridView* view, cudaStream_t stream, const float* pts2 = nullptr,
+               const float* q2 = nullptr, int B2 = 0);
 
 // Cells per cloud.  8192 keeps the binning kernel's shared-memory histogram at 32 KB (4 CTAs per SM)
 // and the cell table L1/L2-friendly; a KITTI-shape cloud at cell = radius needs ~4.6 k cells.
