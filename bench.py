@@ -365,7 +365,7 @@ def run_b200(args, name, wl):
     _, cnt_s = ume.ume_moments(b0["src_pts"], b0["src_kp"], b0["src_feat"], K_NN, RADIUS, return_count=True)
     _, cnt_t = ume.ume_moments(b0["tgt_pts"], b0["tgt_kp"], b0["tgt_feat"], K_NN, RADIUS, return_count=True)
     cnt_s, cnt_t = cnt_s.cpu().numpy(), cnt_t.cpu().numpy()
-    bytes_per_launch = 0.5 * (algorithmic_bytes(cnt_s, wl["n_kp"], wl["C"]) + algorithmic_bytes(cnt_t, wl["n_kp"], wl["C"]))
+    bytes_both_sides = algorithmic_bytes(cnt_s, wl["n_kp"], wl["C"]) + algorithmic_bytes(cnt_t, wl["n_kp"], wl["C"])   # one micro-batch
 
     from umeregrobust_b200.clocks import ClockSampler
     try:
@@ -507,12 +507,16 @@ def run_b200(args, name, wl):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     mom_ms, mom_n = prof["moments"]
     mom_avg_ms = mom_ms / max(mom_n, 1)
+    # launches per micro-batch: 1 when source and target share one launch (ume_moments_pair_f32), else 2
+    mom_per_micro = max(1, int(round(mom_n / float(args.steps * n_micro)))) if mom_n else 1
+    bytes_per_launch = bytes_both_sides / mom_per_micro
     achieved = bytes_per_launch / (mom_avg_ms * 1e-3) / 1e9 if mom_n else None
-    traffic = None
+    traffic = l2_bytes = None
     try:
         tr = json.load(open(os.path.join(REPO, "profiles", "moments_dram_traffic.json")))
-        if tr.get("workload") == name:
+        if tr.get("workload") == name and int(tr.get("launches_per_micro_batch", 2)) == mom_per_micro:
             traffic = tr.get("dram_bytes_per_launch")
+            l2_bytes = tr.get("l2_bytes_per_launch")
     except Exception:
         pass
     stages = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
@@ -542,6 +546,8 @@ def run_b200(args, name, wl):
                      "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
                      "dram_frac": (traffic / (mom_avg_ms * 1e-3) / 1e9 / hbm_peak) if (traffic and mom_n) else None,
+                     "l2_gbs": (l2_bytes / (mom_avg_ms * 1e-3) / 1e9) if (l2_bytes and mom_n) else None,
+                     "launch_covers": "source + target batch" if mom_per_micro == 1 else "one side",
                      "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": mom_avg_ms,
                      "launches_timed": mom_n, "peak_source": peaks_note + " (MEASURED_PEAKS.json hbm_gbs)",
                      "note": "frac counts SURVEY §8d's algorithmic bytes, most of which are served L2->SM (a cloud's features, "

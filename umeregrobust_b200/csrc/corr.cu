@@ -4,8 +4,9 @@
 //
 // Everything is built on one device routine: an exact K-nearest search of one query per THREAD over
 // the search grid (rings of cells of growing Chebyshev radius, stop when the K-th best distance beats
-// the next ring's lower bound), the K best kept sorted by (dist2, row) in a small per-thread array —
-// ties go to the lower row, as a row-order scan with strict '<' does in pytorch3d.
+// the next ring's lower bound), the K best ordered by (dist2, row) — ties go to the lower row, as a row-order
+// scan with strict '<' does in pytorch3d — kept sorted in a per-thread array (knn_points, any K) or unsorted
+// in a shared-memory column with the worst entry tracked (the hypothesis scorer, which only sums over them).
 //
 // Correlation score (pc_corr, utils/loc_utils.py:592-619):
 //   score[h] = (1/Ns) sum_i sum_{k<K} cauchy(|T_h p_i - q_nn(i,k)|; sigma) <wf_src_i, wf_tgt_nn(i,k)>
@@ -62,37 +63,66 @@ struct ArrayTopK {
     }
 };
 
-// K best in REGISTERS (K is a compile-time constant): sorted ascending, empty slots hold +inf.
-// Insertion is one fully unrolled carry pass — no local memory, no data-dependent loop.
+// K best UNSORTED in a shared-memory column (entries `stride` apart), the worst of them tracked through per-group
+// maxima in registers: an insertion overwrites the worst entry, re-reads the S entries of that entry's group and
+// compares G group maxima — ~45 instructions instead of the ~125 of a carry pass through a sorted register list.
+// (Profile of the round-1 kernel: 72 % of all issued instructions were that carry pass, because a warp runs it
+// whenever ANY of its 32 queries inserts.)  Order: (dist2, row) lexicographic, as everywhere.
 template <int K_>
-struct RegTopK {
+struct SmemGroupTopK {
     static constexpr int kCap = K_;
-    float bd[K_];
-    int bj[K_];
-    UME_DEVI void reset(int) {
+    static constexpr int S = 5, G = (K_ + S - 1) / S;
+    float* dcol;
+    int* rcol;
+    int stride, n;
+    float gd[G];                     // per group: the largest (dist2, row) and where it sits
+    int gr[G], gp[G];
+    float wd;                        // the worst of all
+    int wr, wp;
+    UME_DEVI SmemGroupTopK(float* d, int* r, int st) : dcol(d), rcol(r), stride(st), n(0), wd(INFINITY), wr(0x7fffffff), wp(0) {}
+    UME_DEVI void reset(int) { n = 0; wd = INFINITY; wr = 0x7fffffff; wp = 0; }
+    UME_DEVI bool full() const { return n == K_; }
+    UME_DEVI float worst() const { return wd; }
+    UME_DEVI static bool after(float d, int j, float d2, int j2) { return d > d2 || (d == d2 && j > j2); }
+    UME_DEVI void group_max(int g, float& md, int& mr, int& mp) const {
+        md = -1.f; mr = -1; mp = g * S;
 #pragma unroll
-        for (int k = 0; k < K_; ++k) { bd[k] = INFINITY; bj[k] = 0x7fffffff; }
-    }
-    UME_DEVI bool full() const { return bj[K_ - 1] != 0x7fffffff; }
-    UME_DEVI float worst() const { return bd[K_ - 1]; }
-    UME_DEVI void consider(float d, int j) {
-        if (!(d < bd[K_ - 1] || (d == bd[K_ - 1] && j < bj[K_ - 1]))) return;
-#pragma unroll
-        for (int k = 0; k < K_; ++k) {
-            const bool lt = d < bd[k] || (d == bd[k] && j < bj[k]);
-            const float td = lt ? bd[k] : d;
-            const int tj = lt ? bj[k] : j;
-            bd[k] = lt ? d : bd[k];
-            bj[k] = lt ? j : bj[k];
-            d = td;
-            j = tj;
+        for (int i = 0; i < S; ++i) {
+            const int pos = g * S + i;
+            if (pos < K_) {
+                const float e = dcol[pos * stride];
+                const int r = rcol[pos * stride];
+                if (after(e, r, md, mr)) { md = e; mr = r; mp = pos; }
+            }
         }
     }
-    template <typename F>
-    UME_DEVI void for_each(F f) const {
+    UME_DEVI void global_max() {
+        wd = gd[0]; wr = gr[0]; wp = gp[0];
 #pragma unroll
-        for (int k = 0; k < K_; ++k)
-            if (bj[k] != 0x7fffffff) f(bd[k], bj[k]);          // fewer than K rows in the cloud: empty slots
+        for (int g = 1; g < G; ++g)
+            if (after(gd[g], gr[g], wd, wr)) { wd = gd[g]; wr = gr[g]; wp = gp[g]; }
+    }
+    UME_DEVI void consider(float d, int j) {
+        if (n < K_) {
+            dcol[n * stride] = d;
+            rcol[n * stride] = j;
+            if (++n == K_) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) group_max(g, gd[g], gr[g], gp[g]);
+                global_max();
+            }
+            return;
+        }
+        if (!(d < wd || (d == wd && j < wr))) return;
+        dcol[wp * stride] = d;
+        rcol[wp * stride] = j;
+        const int g = wp / S;
+        float md; int mr, mp;
+        group_max(g, md, mr, mp);
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+            if (i == g) { gd[i] = md; gr[i] = mr; gp[i] = mp; }
+        global_max();
     }
 };
 
@@ -254,14 +284,16 @@ struct CorrParams {
 #define UME_CORR_MINB 6            // CTAs per SM the register allocation is capped for
 #endif
 
-template <int C4, typename Top, bool kFma>
+// TopKind: 0 = SmemGroupTopK<20> in the kernel's own neighbour columns (the reference's K), 1 = ArrayTopK<32> (any K <= 32)
+template <int C4, int TopKind, bool kFma>
 __global__ void __launch_bounds__(kCorrThreads, UME_CORR_MINB) corr_score_kernel(CorrParams p) {
-    __shared__ float s_red[kCorrThreads / 32];
-    // the K neighbours of every thread's query, [k][thread]: weight and target row.  The dot products are
-    // then formed by the warp together — C4 lanes per (query, neighbour) read one feature row as one 128-byte
-    // line (one L1 wavefront) instead of 32 lanes gathering 16 bytes from 32 different lines
-    __shared__ float s_w[Top::kCap][kCorrThreads];
-    __shared__ int s_r[Top::kCap][kCorrThreads];
+    constexpr int KCAP = TopKind == 0 ? 20 : 32;
+    // the K neighbours of every thread's query, [k][thread]: squared distance (then weight) and target row.  The
+    // dot products are formed by the warp together — C4 lanes per (query, neighbour) read one feature row as one
+    // 128-byte line (one L1 wavefront) instead of 32 lanes gathering 16 bytes from 32 different lines.  Nothing in
+    // the hypothesis loop synchronises the CTA: every warp writes its own partial sum.
+    __shared__ float s_w[KCAP][kCorrThreads];
+    __shared__ int s_r[KCAP][kCorrThreads];
     const GridHeader hs = p.src_grid.hdr[0];
     const GridHeader ht = p.tgt_grid.hdr[0];
     const int* cs = p.tgt_grid.cell_start;
@@ -275,6 +307,7 @@ __global__ void __launch_bounds__(kCorrThreads, UME_CORR_MINB) corr_score_kernel
     constexpr int PP = 32 / C4;
     const int gq = lane / C4, ch = lane % C4;
     const int K = p.K;
+    const int slot = blockIdx.x * (kCorrThreads / 32) + warp, nslots = gridDim.x * (kCorrThreads / 32);
     for (int hyp = blockIdx.y; hyp < p.n_hyp; hyp += gridDim.y) {
         const float* T = p.T + (size_t)hyp * 16;
         int n_found = 0;
@@ -283,15 +316,21 @@ __global__ void __launch_bounds__(kCorrThreads, UME_CORR_MINB) corr_score_kernel
             const float qx = fmaf(me.z, __ldg(T + 2), fmaf(me.y, __ldg(T + 1), me.x * __ldg(T + 0))) + __ldg(T + 3);
             const float qy = fmaf(me.z, __ldg(T + 6), fmaf(me.y, __ldg(T + 5), me.x * __ldg(T + 4))) + __ldg(T + 7);
             const float qz = fmaf(me.z, __ldg(T + 10), fmaf(me.y, __ldg(T + 9), me.x * __ldg(T + 8))) + __ldg(T + 11);
-            Top top;
-            top.reset(K);
-            grid_knn<kFma>(ht, cs, tgt_sorted, qx, qy, qz, top);
-            top.for_each([&](float dk, int jk) {
-                const float e = sqrtf(dk) * p.inv_sigma;             // |p - q| / sigma
-                s_w[n_found][threadIdx.x] = 1.f / fmaf(e, e, 1.f);   // cauchy_kernel (:588-589)
-                s_r[n_found][threadIdx.x] = jk;
-                ++n_found;
-            });
+            if (TopKind == 0) {
+                SmemGroupTopK<20> top(&s_w[0][threadIdx.x], &s_r[0][threadIdx.x], kCorrThreads);
+                grid_knn<kFma>(ht, cs, tgt_sorted, qx, qy, qz, top);
+                n_found = top.n;
+            } else {
+                ArrayTopK<32> top;
+                top.reset(K);
+                grid_knn<kFma>(ht, cs, tgt_sorted, qx, qy, qz, top);
+                n_found = top.n;
+                for (int k = 0; k < n_found; ++k) { s_w[k][threadIdx.x] = top.bd[k]; s_r[k][threadIdx.x] = top.bj[k]; }
+            }
+            for (int k = 0; k < n_found; ++k) {
+                const float e = sqrtf(s_w[k][threadIdx.x]) * p.inv_sigma;    // |p - q| / sigma
+                s_w[k][threadIdx.x] = 1.f / fmaf(e, e, 1.f);                // cauchy_kernel (:588-589)
+            }
         }
         for (int k = n_found; k < K; ++k) { s_w[k][threadIdx.x] = 0.f; s_r[k][threadIdx.x] = 0; }   // (fewer than K rows in the cloud)
         __syncwarp();
@@ -312,14 +351,8 @@ __global__ void __launch_bounds__(kCorrThreads, UME_CORR_MINB) corr_score_kernel
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(UME_FULL_MASK, acc, o);
-        if (lane == 0) s_red[warp] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float s = 0.f;
-            for (int w = 0; w < kCorrThreads / 32; ++w) s += s_red[w];
-            p.partial[(size_t)hyp * gridDim.x + blockIdx.x] = s;
-        }
-        __syncthreads();
+        if (lane == 0) p.partial[(size_t)hyp * nslots + slot] = acc;
+        __syncwarp();
     }
 }
 
@@ -351,11 +384,11 @@ __global__ void __launch_bounds__(256) corr_finalize_kernel(const float* __restr
     if (threadIdx.x == 0 && best) *best = (s_i[0] == 0x7fffffff) ? 0 : s_i[0];
 }
 
-// K = 20 (the reference's corr_num_nn) keeps the K best in registers; other K use the array version.
+// K = 20 (the reference's corr_num_nn) keeps the K best in the kernel's shared-memory columns; other K use the array version.
 template <int C4, bool kFma>
 void launch_corr_c(const CorrParams& p, int K, dim3 grid, cudaStream_t stream) {
-    if (K == 20) corr_score_kernel<C4, RegTopK<20>, kFma><<<grid, kCorrThreads, 0, stream>>>(p);
-    else corr_score_kernel<C4, ArrayTopK<32>, kFma><<<grid, kCorrThreads, 0, stream>>>(p);
+    if (K == 20) corr_score_kernel<C4, 0, kFma><<<grid, kCorrThreads, 0, stream>>>(p);
+    else corr_score_kernel<C4, 1, kFma><<<grid, kCorrThreads, 0, stream>>>(p);
 }
 void launch_corr(const CorrParams& p, int C, int K, bool fma, dim3 grid, cudaStream_t stream) {
     if (C == 32) {
@@ -454,7 +487,7 @@ extern "C" int ume_weight_features_f32(const float* f, const float* mean, const 
 
 extern "C" size_t ume_corr_scores_workspace_bytes(int Ns, int Nt, int n_hyp) {
     if (Ns <= 0 || Nt <= 0 || n_hyp <= 0) return 0;
-    const size_t nb = (size_t)(Ns + ume::kCorrThreads - 1) / ume::kCorrThreads;
+    const size_t nb = ((size_t)(Ns + ume::kCorrThreads - 1) / ume::kCorrThreads) * (ume::kCorrThreads / 32);   // one partial per warp
     return ume::grid_workspace_bytes(1, Ns, ume::kCellsCap) + ume::grid_workspace_bytes(1, Nt, ume::kCellsCap) +
            ume::align_up((size_t)n_hyp * nb * sizeof(float), 256) + 1024;
 }
@@ -481,7 +514,8 @@ extern "C" int ume_corr_scores_f32(const float* src_pts, const float* tgt_pts, c
     rc = grid_build(tgt_pts, tgt_pts, 1, Nt, Nt, 0.f, -UME_CORR_TGT_PPC(K), kCellsCap, w, &p.tgt_grid, stream);
     if (rc != UME_OK) return rc;
     const int nb = (Ns + kCorrThreads - 1) / kCorrThreads;
-    p.partial = w.take<float>((size_t)n_hyp * nb);
+    const int nslots = nb * (kCorrThreads / 32);                      // one partial sum per warp
+    p.partial = w.take<float>((size_t)n_hyp * nslots);
     UME_REQUIRE(w.ok(), UME_ERR_WORKSPACE, "ume_corr_scores_f32: workspace too small");
     p.wf_src = wf_src; p.wf_tgt = wf_tgt; p.T = T; p.n_hyp = n_hyp; p.K = K; p.inv_sigma = 1.f / sigma;
     // hypothesis groups: enough CTAs for ~8 waves of the 148 SMs
@@ -491,7 +525,7 @@ extern "C" int ume_corr_scores_f32(const float* src_pts, const float* tgt_pts, c
     const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
     ProfScope prof(UME_PROF_CORR, stream);
     launch_corr(p, C, K, fma, grid, stream);
-    corr_finalize_kernel<<<1, 256, 0, stream>>>(p.partial, n_hyp, nb, 1.f / (float)Ns, score, best);
+    corr_finalize_kernel<<<1, 256, 0, stream>>>(p.partial, n_hyp, nslots, 1.f / (float)Ns, score, best);
     count_launch(2);
     return check_launch("corr_score_kernel");
 }
