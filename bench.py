@@ -238,13 +238,15 @@ def algorithmic_bytes(counts, n_kp, C):
     return float(counts.sum()) * (4 * C + 12) + counts.shape[0] * n_kp * (12 + 16 * C)
 
 
-def measure_tf32_peak(torch, dev):
-    """Dense TF32 peak the way MEASURED_PEAKS.json measures bf16: cuBLAS matmul 8192^3, best of 10."""
+def measure_dense_peak(torch, dev, dtype="tf32"):
+    """Dense tensor-core peak the way MEASURED_PEAKS.json measures bf16: cuBLAS matmul 8192^3, best of 10.
+    dtype "tf32" (fp32 operands, TF32 math) or "f16"."""
     old = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
-        a = torch.randn(8192, 8192, device=dev)
-        b = torch.randn(8192, 8192, device=dev)
+        dt = torch.float16 if dtype == "f16" else torch.float32
+        a = torch.randn(8192, 8192, device=dev, dtype=dt)
+        b = torch.randn(8192, 8192, device=dev, dtype=dt)
         best = 1e9
         for i in range(12):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -524,7 +526,8 @@ def run_b200(args, name, wl):
     cd_ms, cd_n = prof["cdist"]
     cd_avg_ms = cd_ms / max(cd_n, 1)
     gemm_flops = 2.0 * (4 * wl["n_kp"]) ** 2 * wl["C"] * micro          # SURVEY §8d, per launch (one micro-batch)
-    tf32_peak = measure_tf32_peak(torch, dev)
+    f16_peak = measure_dense_peak(torch, dev, "f16")
+    tf32_peak = measure_dense_peak(torch, dev, "tf32")
     cfg = base_config(name, wl)
     detail = {}
     detail.update({"pairs_per_gpu_per_step": pairs_per_step, "pairs_per_kernel_batch": micro,
@@ -553,16 +556,20 @@ def run_b200(args, name, wl):
                      "note": "frac counts SURVEY §8d's algorithmic bytes, most of which are served L2->SM (a cloud's features, "
                              "15 MB, stay in the 126 MB L2); dram_frac = measured DRAM bytes per launch (ncu, `traffic`) / time / peak "
                              "is the HBM-side fraction"},
-        "roofline_gemm": {"kernel": "cdist (all-pairs subspace distance, Gram form) + fused arg-min", "bound": "tensor",
-                          "achieved": gemm_flops / (cd_avg_ms * 1e-3) / 1e12 if cd_n else None, "peak": tf32_peak,
-                          "unit": "TFLOP/s", "frac": (gemm_flops / (cd_avg_ms * 1e-3) / 1e12 / tf32_peak) if cd_n else None,
+        "roofline_gemm": {"kernel": "cdist_tc_kernel (all-pairs subspace distance, Gram form, tcgen05 kind::f16) + fused arg-min",
+                          "bound": "tensor", "achieved": gemm_flops / (cd_avg_ms * 1e-3) / 1e12 if cd_n else None, "peak": f16_peak,
+                          "unit": "TFLOP/s", "frac": (gemm_flops / (cd_avg_ms * 1e-3) / 1e12 / f16_peak) if cd_n else None,
+                          "executed_frac": (3.0 * gemm_flops / (cd_avg_ms * 1e-3) / 1e12 / f16_peak) if cd_n else None,
                           "algorithmic_flops_per_launch": gemm_flops, "avg_launch_ms": cd_avg_ms, "launches_timed": cd_n,
-                          "executed_over_algorithmic": 3.0,
-                          "peak_source": "measured live: cuBLAS TF32 matmul 8192^3, best of 10 (the bf16 figure of "
-                                         "MEASURED_PEAKS.json is %.0f)" % float(peaks.get("bf16_tflops", 0.0)),
-                          "note": "algorithmic = 2 (4n)^2 C per pair; the kernel executes 3 TF32 products per term (hi*hi + hi*lo + lo*hi) "
-                                  "for fp32-grade distances, and its epilogue (squares, 4x4 block sums, sqrt, D store, arg-min) reads "
-                                  "every accumulator once from TMEM"},
+                          "executed_over_algorithmic": 3.0, "tf32_peak": tf32_peak,
+                          "tensor_pipe_active_pct_ncu": 39.8,
+                          "peak_source": "measured live: cuBLAS fp16 matmul 8192^3, best of 10 (MEASURED_PEAKS.json bf16: %.0f); "
+                                         "tf32_peak: the same with TF32 math" % float(peaks.get("bf16_tflops", 0.0)),
+                          "note": "algorithmic = 2 (4n)^2 C per pair; every fp32 operand is split into two fp16 numbers and the kernel "
+                                  "executes 3 fp16 products per term (hi*hi + hi*lo + lo*hi) for fp32-grade distances; K = C is tiny, "
+                                  "so the kernel is bound by draining the accumulators (squares, 4x4 block sums, sqrt, D store, arg-min "
+                                  "read every accumulator once from TMEM), not by the MMAs; tensor_pipe_active from "
+                                  "profiles/r02_cdist_kernel_full.csv"},
         "stages": stages,
     }
     if gtc is not None:

@@ -213,6 +213,21 @@ def test_hot_path_against_reference_golden(ume, golden, name):
     clear = (srt[..., 1] - srt[..., 0]) > 1e-4
     assert clear.mean() > 0.9
     assert np.array_equal(host(am)[clear], g["match"][..., 1][clear])
+    # the remaining rows (best and second best closer than 1e-4 in fp64): every disagreement with the reference's
+    # arg-min must be a choice between candidates the fp64 oracle itself cannot tell apart at fp32 resolution —
+    # the picked column's fp64 distance is within the reference's own cdist noise (1.5e-3 near D = 0) of the best —
+    # and the count is reported (it goes to DESIGN.md §3.2)
+    unclear = ~clear
+    mine, ref = host(am)[unclear], g["match"][..., 1][unclear]
+    flips = mine != ref
+    d_unclear = D64[unclear]
+    best = d_unclear.min(-1)
+    excess_mine = d_unclear[np.arange(len(mine)), mine] - best
+    excess_ref = d_unclear[np.arange(len(ref)), ref] - best
+    print("arg-min vs the reference on the %d unclear rows of %d: %d flips; fp64 excess over the true minimum: ours max %.2e, "
+          "the reference's max %.2e" % (int(unclear.sum()), unclear.size, int(flips.sum()), float(excess_mine.max(initial=0)),
+                                       float(excess_ref.max(initial=0))))
+    assert float(excess_mine.max(initial=0)) <= max(2e-3, 2 * float(excess_ref.max(initial=0)))
     assert np.array_equal(host(am), np.argmin(D, -1))        # fused arg-min == arg-min of the written D
     assert np.abs(host(dm) - D.min(-1)).max() == 0
     # rigid hypotheses from the reference's matched matrices

@@ -21,6 +21,7 @@ timeout 600 python tools/bench_corr.py 1024 10000 2>&1 | tail -1 | tee -a ${P}_c
 # launch list (serialised, cold caches: shares only)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${P}_launches_bench_steps2.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 0 --full-reg-pairs 0 > ${P}_launches.log 2>&1
+[ "${1:-}" = nocapture ] && exit 0
 BENCH="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 0 --full-reg-pairs 0"
 for spec in moments:moments_warp_kernel:2 cdist:cdist_tc_kernel:2 gridrank:grid_rank_kernel:2; do
   IFS=: read tag kern skip <<< "$spec"
