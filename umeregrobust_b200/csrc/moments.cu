@@ -87,6 +87,7 @@ struct VecAcc {
                 const float4 v = seg[in ? i + lane : 0];
                 const bool keep = in && __float_as_int(v.w) <= T;
                 const unsigned m = __ballot_sync(UME_FULL_MASK, keep);
+                __syncwarp();                  // every lane's read of this round is done before any lane overwrites a slot
                 if (keep) seg[out + __popc(m & lt)] = v;
                 out += __popc(m);
             }
