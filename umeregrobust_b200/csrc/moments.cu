@@ -84,7 +84,8 @@ struct VecAcc {
             int out = 0;
             for (int i = 0; i < cnt; i += 32) {
                 const bool in = i + lane < cnt;
-                const float4 v = seg[in ? i + lane : 0];
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (in) v = seg[i + lane];          // (lanes past the end read nothing: slot 0 may be rewritten by now)
                 const bool keep = in && __float_as_int(v.w) <= T;
                 const unsigned m = __ballot_sync(UME_FULL_MASK, keep);
                 __syncwarp();                  // every lane's read of this round is done before any lane overwrites a slot
