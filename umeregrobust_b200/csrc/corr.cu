@@ -65,63 +65,67 @@ struct ArrayTopK {
 
 // K best UNSORTED in a shared-memory column (entries `stride` apart), the worst of them tracked through per-group
 // maxima in registers: an insertion overwrites the worst entry, re-reads the S entries of that entry's group and
-// compares G group maxima — ~45 instructions instead of the ~125 of a carry pass through a sorted register list.
+// compares G group maxima — ~30 instructions instead of the ~125 of a carry pass through a sorted register list.
 // (Profile of the round-1 kernel: 72 % of all issued instructions were that carry pass, because a warp runs it
-// whenever ANY of its 32 queries inserts.)  Order: (dist2, row) lexicographic, as everywhere.
+// whenever ANY of its 32 queries inserts.)  An entry is ONE 64-bit key, (dist2 bits << 32) | row: squared distances
+// are non-negative, so unsigned key order is the (dist2, row) lexicographic order used everywhere — one compare,
+// one shared-memory access per entry, ties by row for free.
 template <int K_>
 struct SmemGroupTopK {
     static constexpr int kCap = K_;
     static constexpr int S = 5, G = (K_ + S - 1) / S;
-    float* dcol;
-    int* rcol;
+    unsigned long long* col;
     int stride, n;
-    float gd[G];                     // per group: the largest (dist2, row) and where it sits
-    int gr[G], gp[G];
-    float wd;                        // the worst of all
-    int wr, wp;
-    UME_DEVI SmemGroupTopK(float* d, int* r, int st) : dcol(d), rcol(r), stride(st), n(0), wd(INFINITY), wr(0x7fffffff), wp(0) {}
-    UME_DEVI void reset(int) { n = 0; wd = INFINITY; wr = 0x7fffffff; wp = 0; }
+    unsigned long long gkey[G];      // per group: the largest key and where it sits
+    int gp[G];
+    unsigned long long wkey;         // the worst of all
+    int wp;
+    float wd;
+    UME_DEVI SmemGroupTopK(unsigned long long* c, int st) : col(c), stride(st), n(0), wkey(~0ull), wp(0), wd(INFINITY) {}
+    UME_DEVI void reset(int) { n = 0; wkey = ~0ull; wp = 0; wd = INFINITY; }
     UME_DEVI bool full() const { return n == K_; }
     UME_DEVI float worst() const { return wd; }
-    UME_DEVI static bool after(float d, int j, float d2, int j2) { return d > d2 || (d == d2 && j > j2); }
-    UME_DEVI void group_max(int g, float& md, int& mr, int& mp) const {
-        md = -1.f; mr = -1; mp = g * S;
+    UME_DEVI static unsigned long long pack(float d, int j) {
+        return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j;
+    }
+    UME_DEVI void group_max(int g, unsigned long long& mk, int& mp) const {
+        mp = g * S;
+        mk = col[mp * stride];
 #pragma unroll
-        for (int i = 0; i < S; ++i) {
+        for (int i = 1; i < S; ++i) {
             const int pos = g * S + i;
             if (pos < K_) {
-                const float e = dcol[pos * stride];
-                const int r = rcol[pos * stride];
-                if (after(e, r, md, mr)) { md = e; mr = r; mp = pos; }
+                const unsigned long long e = col[pos * stride];
+                if (e > mk) { mk = e; mp = pos; }
             }
         }
     }
     UME_DEVI void global_max() {
-        wd = gd[0]; wr = gr[0]; wp = gp[0];
+        wkey = gkey[0]; wp = gp[0];
 #pragma unroll
         for (int g = 1; g < G; ++g)
-            if (after(gd[g], gr[g], wd, wr)) { wd = gd[g]; wr = gr[g]; wp = gp[g]; }
+            if (gkey[g] > wkey) { wkey = gkey[g]; wp = gp[g]; }
+        wd = __uint_as_float((unsigned)(wkey >> 32));
     }
     UME_DEVI void consider(float d, int j) {
+        const unsigned long long key = pack(d, j);
         if (n < K_) {
-            dcol[n * stride] = d;
-            rcol[n * stride] = j;
+            col[n * stride] = key;
             if (++n == K_) {
 #pragma unroll
-                for (int g = 0; g < G; ++g) group_max(g, gd[g], gr[g], gp[g]);
+                for (int g = 0; g < G; ++g) group_max(g, gkey[g], gp[g]);
                 global_max();
             }
             return;
         }
-        if (!(d < wd || (d == wd && j < wr))) return;
-        dcol[wp * stride] = d;
-        rcol[wp * stride] = j;
+        if (!(key < wkey)) return;
+        col[wp * stride] = key;
         const int g = wp / S;
-        float md; int mr, mp;
-        group_max(g, md, mr, mp);
+        unsigned long long mk; int mp;
+        group_max(g, mk, mp);
 #pragma unroll
         for (int i = 0; i < G; ++i)
-            if (i == g) { gd[i] = md; gr[i] = mr; gp[i] = mp; }
+            if (i == g) { gkey[i] = mk; gp[i] = mp; }
         global_max();
     }
 };
@@ -292,8 +296,7 @@ __global__ void __launch_bounds__(kCorrThreads, UME_CORR_MINB) corr_score_kernel
     // dot products are formed by the warp together — C4 lanes per (query, neighbour) read one feature row as one
     // 128-byte line (one L1 wavefront) instead of 32 lanes gathering 16 bytes from 32 different lines.  Nothing in
     // the hypothesis loop synchronises the CTA: every warp writes its own partial sum.
-    __shared__ float s_w[KCAP][kCorrThreads];
-    __shared__ int s_r[KCAP][kCorrThreads];
+    __shared__ unsigned long long s_key[KCAP][kCorrThreads];   // (dist2 bits, then weight bits) << 32 | target row
     const GridHeader hs = p.src_grid.hdr[0];
     const GridHeader ht = p.tgt_grid.hdr[0];
     const int* cs = p.tgt_grid.cell_start;
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(kCorrThreads, UME_CORR_MINB) corr_score_kernel
             const float qy = fmaf(me.z, __ldg(T + 6), fmaf(me.y, __ldg(T + 5), me.x * __ldg(T + 4))) + __ldg(T + 7);
             const float qz = fmaf(me.z, __ldg(T + 10), fmaf(me.y, __ldg(T + 9), me.x * __ldg(T + 8))) + __ldg(T + 11);
             if (TopKind == 0) {
-                SmemGroupTopK<20> top(&s_w[0][threadIdx.x], &s_r[0][threadIdx.x], kCorrThreads);
+                SmemGroupTopK<20> top(&s_key[0][threadIdx.x], kCorrThreads);
                 grid_knn<kFma>(ht, cs, tgt_sorted, qx, qy, qz, top);
                 n_found = top.n;
             } else {
@@ -325,14 +328,15 @@ __global__ void __launch_bounds__(kCorrThreads, UME_CORR_MINB) corr_score_kernel
                 top.reset(K);
                 grid_knn<kFma>(ht, cs, tgt_sorted, qx, qy, qz, top);
                 n_found = top.n;
-                for (int k = 0; k < n_found; ++k) { s_w[k][threadIdx.x] = top.bd[k]; s_r[k][threadIdx.x] = top.bj[k]; }
+                for (int k = 0; k < n_found; ++k) s_key[k][threadIdx.x] = SmemGroupTopK<20>::pack(top.bd[k], top.bj[k]);
             }
             for (int k = 0; k < n_found; ++k) {
-                const float e = sqrtf(s_w[k][threadIdx.x]) * p.inv_sigma;    // |p - q| / sigma
-                s_w[k][threadIdx.x] = 1.f / fmaf(e, e, 1.f);                // cauchy_kernel (:588-589)
+                const unsigned long long e = s_key[k][threadIdx.x];
+                const float r = sqrtf(__uint_as_float((unsigned)(e >> 32))) * p.inv_sigma;       // |p - q| / sigma
+                s_key[k][threadIdx.x] = ((unsigned long long)__float_as_uint(1.f / fmaf(r, r, 1.f)) << 32) | (e & 0xffffffffull);   // cauchy_kernel (:588-589)
             }
         }
-        for (int k = n_found; k < K; ++k) { s_w[k][threadIdx.x] = 0.f; s_r[k][threadIdx.x] = 0; }   // (fewer than K rows in the cloud)
+        for (int k = n_found; k < K; ++k) s_key[k][threadIdx.x] = 0ull;   // (fewer than K rows in the cloud: weight 0, row 0)
         __syncwarp();
         float acc = 0.f;
         for (int q = 0; q < 32; ++q) {
@@ -342,8 +346,9 @@ __global__ void __launch_bounds__(kCorrThreads, UME_CORR_MINB) corr_score_kernel
 #pragma unroll 5
             for (int k0 = 0; k0 < K; k0 += PP) {
                 const int k = min(k0 + gq, K - 1);
-                const float wgt = (k0 + gq < K) ? s_w[k][col] : 0.f;
-                const float4 g = ldg_f4(p.wf_tgt + (size_t)s_r[k][col] * (C4 * 4) + 4 * ch);
+                const unsigned long long e = s_key[k][col];
+                const float wgt = (k0 + gq < K) ? __uint_as_float((unsigned)(e >> 32)) : 0.f;
+                const float4 g = ldg_f4(p.wf_tgt + (size_t)(unsigned)(e & 0xffffffffull) * (C4 * 4) + 4 * ch);
                 float v = a.x * g.x;
                 v = fmaf(a.y, g.y, v); v = fmaf(a.z, g.z, v); v = fmaf(a.w, g.w, v);
                 acc = fmaf(v, wgt, acc);
