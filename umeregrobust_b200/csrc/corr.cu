@@ -251,6 +251,45 @@ __global__ void __launch_bounds__(128) spatial_var_kernel(GridView grid, const f
     out[(size_t)b * N + i] = (top.n > 1) ? acc / (float)(top.n - 1) : 0.f;
 }
 
+// The reference's knn = 50 (utils/loc_utils.py:647-648): the K best unsorted in a shared-memory column (SmemGroupTopK)
+// instead of a sorted per-thread array in local memory; the nearest entry (the one the reference drops as index 0 of
+// the sorted list) is the minimum key.
+template <int K_, bool kFma>
+__global__ void __launch_bounds__(128) spatial_var_smem_kernel(GridView grid, const float* __restrict__ feat, int C,
+                                                               float* __restrict__ out) {
+    extern __shared__ unsigned long long sv_keys[];          // [K_][128]
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = grid.N;
+    const GridHeader h = grid.hdr[b];
+    if (t >= h.n_sorted) return;
+    const int* cs = grid.cell_start + (size_t)b * (grid.cells_cap + 1);
+    const float4* sorted_b = grid.sorted + (size_t)b * N;
+    const float4 me = sorted_b[t];
+    const int i = __float_as_int(me.w);
+    unsigned long long* col = sv_keys + threadIdx.x;
+    SmemGroupTopK<K_> top(col, 128);
+    grid_knn<kFma>(h, cs, sorted_b, me.x, me.y, me.z, top);
+    unsigned long long kmin = ~0ull;
+    for (int k = 0; k < top.n; ++k) kmin = min(kmin, col[k * 128]);
+    const float* fb = feat + (size_t)b * N * C;
+    const float* fi = fb + (size_t)i * C;
+    float acc = 0.f;
+    for (int k = 0; k < top.n; ++k) {
+        const unsigned long long e = col[k * 128];
+        if (e == kmin) continue;                               // (keys are distinct: one entry per target row)
+        const float* fj = fb + (size_t)(unsigned)(e & 0xffffffffull) * C;
+        float s = 0.f;
+        for (int c = 0; c < C; c += 4) {
+            const float4 a = ldg_f4(fi + c), v = ldg_f4(fj + c);
+            const float dx = a.x - v.x, dy = a.y - v.y, dz = a.z - v.z, dw = a.w - v.w;
+            s = fmaf(dx, dx, s); s = fmaf(dy, dy, s); s = fmaf(dz, dz, s); s = fmaf(dw, dw, s);
+        }
+        acc += sqrtf(s);
+    }
+    out[(size_t)b * N + i] = (top.n > 1) ? acc / (float)(top.n - 1) : 0.f;
+}
+
 // ---------------------------------------------------------------- weighted features
 // wf[i,:] = (f[i,:] - m[:]) * w[i]   (utils/loc_utils.py:649-650)
 __global__ void weight_features_kernel(const float* __restrict__ f, const float* __restrict__ m, const float* __restrict__ w,
@@ -471,7 +510,13 @@ extern "C" int ume_feature_spatial_var_f32(const float* pts, const float* feat, 
     UME_REQUIRE(me == cudaSuccess, UME_ERR_CUDA, "ume_feature_spatial_var_f32: cudaMemsetAsync: %s", cudaGetErrorString(me));
     dim3 grid((unsigned)((N + 127) / 128), (unsigned)B);
     const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
-    if (fma) spatial_var_kernel<64, true><<<grid, 128, 0, stream>>>(g, feat, C, knn, out);
+    if (knn == 50) {
+        const size_t smem = (size_t)50 * 128 * sizeof(unsigned long long);
+        auto kern = fma ? spatial_var_smem_kernel<50, true> : spatial_var_smem_kernel<50, false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        UME_REQUIRE(e == cudaSuccess, UME_ERR_CUDA, "ume_feature_spatial_var_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        kern<<<grid, 128, smem, stream>>>(g, feat, C, out);
+    } else if (fma) spatial_var_kernel<64, true><<<grid, 128, 0, stream>>>(g, feat, C, knn, out);
     else spatial_var_kernel<64, false><<<grid, 128, 0, stream>>>(g, feat, C, knn, out);
     count_launch();
     return check_launch("spatial_var_kernel");
