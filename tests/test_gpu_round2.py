@@ -412,11 +412,21 @@ def test_pair_launch_is_bit_identical_to_two_launches(ume, C, n):
     G1, Gc1, G2, Gc2, both = pair
     assert torch.equal(G1, F1) and torch.equal(Gc1, Fc1) and torch.equal(G2, F2) and torch.equal(Gc2, Fc2)
     assert both.shape[0] == 4 and both.data_ptr() == Gc1.data_ptr()
+    # ... and with the CTA-per-keypoint kernel (what small launches get): bit-identical to two CTA-kernel launches
+    ume.config["cta_moments"] = True
+    try:
+        H1, Hc1 = ume.ume_moments(d["src_pts"], d["src_kp"], d["src_feat"], 750, 5.0, return_centered=True)
+        H2, Hc2 = ume.ume_moments(d["tgt_pts"], d["tgt_kp"], d["tgt_feat"], 750, 5.0, return_centered=True)
+        P1, Pc1, P2, Pc2, _ = ume.ume_moments_pair(d["src_pts"], d["src_kp"], d["src_feat"], d["tgt_pts"], d["tgt_kp"], d["tgt_feat"],
+                                                   750, 5.0, return_centered=True)
+    finally:
+        ume.config["cta_moments"] = False
+    assert torch.equal(P1, H1) and torch.equal(Pc1, Hc1) and torch.equal(P2, H2) and torch.equal(Pc2, Hc2)
     # different shapes on the two sides: the pair entry declines, the step falls back to two launches
     assert ume.ume_moments_pair(d["src_pts"], d["src_kp"], d["src_feat"], d["tgt_pts"][:, :-8], d["tgt_kp"], d["tgt_feat"][:, :-8],
                                 750, 5.0) is None
     out = ume.register_hypotheses(d["src_pts"], d["src_feat"], d["src_kp"], d["tgt_pts"], d["tgt_feat"], d["tgt_kp"], 750, 5.0, want_D=True)
-    ume.config["cta_moments"] = True             # the pair entry declines: two launches of the CTA kernel
+    ume.config["cta_moments"] = True             # the pair entry with the CTA-per-keypoint kernel
     try:
         ref = ume.register_hypotheses(d["src_pts"], d["src_feat"], d["src_kp"], d["tgt_pts"], d["tgt_feat"], d["tgt_kp"], 750, 5.0, want_D=True)
     finally:

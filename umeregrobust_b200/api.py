@@ -236,20 +236,17 @@ def ume_moments(pts, kpts, feat, K, radius, return_centered=False, return_count=
     return out[0] if len(out) == 1 else out
 
 
-WARP_KERNEL_MIN_KEYPOINTS = 3072      # below this a launch is faster on the CTA-per-keypoint kernel (csrc/moments.cu)
-
-
 def ume_moments_pair(pts1, kpts1, feat1, pts2, kpts2, feat2, K, radius, return_centered=False, buf=None):
     """`ume_moments` of a source and a target batch in ONE search-grid build and ONE kernel launch
     (`ume_moments_pair_f32`): returns (F1, F2, F_both) or (F1, Fc1, F2, Fc2, Fc_both) — the per-side results are
     the halves of one (2B,n,C,4) allocation (the last element), bit-identical to two `ume_moments` calls.  Returns None when the pair entry does not apply (different
     shapes on the two sides, a channel count or a launch size the warp-per-keypoint kernel is not used for)."""
-    if config["cta_moments"] is True or tuple(pts1.shape) != tuple(pts2.shape) or tuple(kpts1.shape) != tuple(kpts2.shape) \
+    if tuple(pts1.shape) != tuple(pts2.shape) or tuple(kpts1.shape) != tuple(kpts2.shape) \
             or tuple(feat1.shape) != tuple(feat2.shape) or feat1.dim() != 3:
         return None
     B, N, _ = pts1.shape
     n, C = kpts1.shape[1], feat1.shape[2]
-    if C not in (16, 32, 64, 128) or (2 * B * n < WARP_KERNEL_MIN_KEYPOINTS and not config.get("warp_moments")) or 2 * B > 65535:
+    if C not in (16, 32, 64, 128) or 2 * B > 65535:
         return None
     pts1, kpts1, feat1 = _dev_f32(pts1, "pts1", 3), _dev_f32(kpts1, "kpts1", 3), _dev_f32(feat1, "feat1", 3)
     pts2, kpts2, feat2 = _dev_f32(pts2, "pts2", 3), _dev_f32(kpts2, "kpts2", 3), _dev_f32(feat2, "feat2", 3)

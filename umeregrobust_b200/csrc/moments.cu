@@ -35,6 +35,9 @@ struct MomentsParams {
     float* F;             // (B,n,C,4)
     float* Fc;            // (B,n,C,4) or null
     int32_t* count;       // (B,n) or null
+    const float* kpts2;   // clouds [Bs, B): keypoints / features of a second batch handled by the same launch
+    const float* feat2;   //   (null and Bs = B for a single batch)
+    int Bs;
     int n, C, K, cap;
     float radius;
 };
@@ -190,8 +193,9 @@ __global__ void __launch_bounds__(kNT, UME_MOMENTS_MINB) moments_kernel(MomentsP
     const GridHeader h = p.grid.hdr[b];
     const int* cs = p.grid.cell_start + (size_t)b * (p.grid.cells_cap + 1);
     const float4* sorted_b = p.grid.sorted + (size_t)b * p.grid.N;
-    const float* feat_b = p.feat + (size_t)b * p.grid.N * C;
-    const float kx = p.kpts[(size_t)q * 3 + 0], ky = p.kpts[(size_t)q * 3 + 1], kz = p.kpts[(size_t)q * 3 + 2];
+    const float* feat_b = (b < p.Bs) ? p.feat + (size_t)b * p.grid.N * C : p.feat2 + (size_t)(b - p.Bs) * p.grid.N * C;
+    const float* kp = (b < p.Bs) ? p.kpts + (size_t)q * 3 : p.kpts2 + ((size_t)q - (size_t)p.Bs * p.n) * 3;
+    const float kx = kp[0], ky = kp[1], kz = kp[2];
 
     Acc acc;
     acc.clear();
@@ -299,6 +303,7 @@ extern "C" int ume_moments_f32(const float* pts, const float* kpts, const float*
     int rc = grid_build(pts, kpts, B, N, n, fabsf(radius), cell, kCellsCap, w, &p.grid, stream);
     if (rc != UME_OK) return rc;
     p.kpts = kpts; p.feat = feat; p.F = F; p.Fc = Fc; p.count = count;
+    p.kpts2 = nullptr; p.feat2 = nullptr; p.Bs = B;
     p.n = n; p.C = C; p.K = K; p.cap = moments_cap(C, K); p.radius = radius;
     const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
     if (use_warp) {
@@ -332,7 +337,7 @@ extern "C" int ume_moments_f32(const float* pts, const float* kpts, const float*
 }
 
 // Source and target batch of a registration step in ONE grid build and ONE moment launch: 2B clouds, no tail
-// between the two sides, half the launches.  Warp-per-keypoint kernel only.
+// between the two sides, half the launches.  Kernel choice as in ume_moments_f32.
 extern "C" int ume_moments_pair_f32(const float* pts1, const float* kpts1, const float* feat1, const float* pts2,
                                     const float* kpts2, const float* feat2, int B, int N, int n, int C, int K, float radius,
                                     unsigned flags, float* F, float* Fc, int32_t* count, void* ws, size_t ws_bytes,
@@ -352,18 +357,38 @@ extern "C" int ume_moments_pair_f32(const float* pts1, const float* kpts1, const
                 "ume_moments_pair_f32: workspace too small (%zu needed, %zu given)", ume_moments_workspace_bytes(2 * B, N, n, C, K),
                 ws_bytes);
     Workspace w(ws, ws_bytes);
+    const bool raw = (flags & UME_FLAG_RAW_MOMENTS) != 0;
+    const bool fma = (flags & UME_FLAG_FMA_DIST) != 0;
+    // launches too small to fill the warp slots are faster on the CTA-per-keypoint kernel (see ume_moments_f32)
+    const bool small = (long long)2 * B * n < kWarpKernelMinKeypoints;
+    const bool use_warp = !((flags & UME_FLAG_CTA_MOMENTS) || (small && !(flags & UME_FLAG_WARP_MOMENTS))) || raw;
+    if (!use_warp) {
+        MomentsParams p;
+        const float cell = fabsf(radius) / ((flags & UME_FLAG_CELL_DIV2) ? 2.f : 1.f);
+        int rc = grid_build(pts1, kpts1, B, N, n, fabsf(radius), cell, kCellsCap, w, &p.grid, stream, pts2, kpts2, B);
+        if (rc != UME_OK) return rc;
+        p.kpts = kpts1; p.feat = feat1; p.kpts2 = kpts2; p.feat2 = feat2; p.Bs = B;
+        p.F = F; p.Fc = Fc; p.count = count;
+        p.n = n; p.C = C; p.K = K; p.cap = moments_cap(C, K); p.radius = radius;
+        switch (C) {
+            case 16: return launch_moments<VecAcc<4>>(p, 2 * B, fma, stream);
+            case 32: return launch_moments<VecAcc<8>>(p, 2 * B, fma, stream);
+            case 64: return launch_moments<VecAcc<16>>(p, 2 * B, fma, stream);
+            default: return launch_moments<VecAcc<32>>(p, 2 * B, fma, stream);
+        }
+    }
     warpk::Params wp;
     int rc = grid_build(pts1, kpts1, B, N, n, fabsf(radius), fabsf(radius) / (float)UME_WARPK_CELL_DIV, kCellsCap, w, &wp.grid,
                         stream, pts2, kpts2, B);
     if (rc != UME_OK) return rc;
     wp.kpts = kpts1; wp.feat = feat1; wp.kpts2 = kpts2; wp.feat2 = feat2; wp.Bs = B;
     wp.F = F; wp.Fc = Fc; wp.count = count;
-    wp.gF = nullptr; wp.grad_feat = nullptr; wp.raw = (flags & UME_FLAG_RAW_MOMENTS) ? 1 : 0;
+    wp.gF = nullptr; wp.grad_feat = nullptr; wp.raw = raw ? 1 : 0;
     wp.n = n; wp.K = K; wp.total = (long long)2 * B * n; wp.radius = radius;
     wp.next = w.take<unsigned long long>(1);
     UME_REQUIRE(w.ok(), UME_ERR_WORKSPACE, "ume_moments_pair_f32: workspace too small for the work counter");
     ProfScope prof(UME_PROF_MOMENTS, stream);
-    return warpk::launch_c<warpk::kForward>(wp, C, (flags & UME_FLAG_FMA_DIST) != 0, stream);
+    return warpk::launch_c<warpk::kForward>(wp, C, fma, stream);
 }
 
 // Shared front end of the two auxiliary entry points below (same checks and grid as ume_moments_f32).
