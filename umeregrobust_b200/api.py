@@ -550,8 +550,13 @@ class ume_kp_layer(torch.nn.Module):
     def forward(self, source_points, source_features, source_kp, target_points, target_features, target_kp):
         bs, n_kp = source_kp.shape[0], source_kp.shape[1]
         # :383-393 ball_query + gathers + ume_mat, fused (no (bs,n_kp,K,C) tensor)
-        G = ume_moments(source_points, source_kp, source_features, self.ume_knn, self.ume_desc_rad)
-        H = ume_moments(target_points, target_kp, target_features, self.ume_knn, self.ume_desc_rad)
+        pair = ume_moments_pair(source_points, source_kp, source_features, target_points, target_kp, target_features,
+                                self.ume_knn, self.ume_desc_rad)              # one grid build + one launch for both sides
+        if pair is not None:
+            G, H, _ = pair
+        else:
+            G = ume_moments(source_points, source_kp, source_features, self.ume_knn, self.ume_desc_rad)
+            H = ume_moments(target_points, target_kp, target_features, self.ume_knn, self.ume_desc_rad)
         C = G.shape[-2]
         if self.n_rand is not None:
             # :406-410 random triplet sums (host RNG, "only valid for batch size of one")
